@@ -1,0 +1,49 @@
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    # gpu-marked tests are skipped (not failed) when no device is visible and they were not deselected
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    def _load(name):
+        return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+    return _load
+
+
+@pytest.fixture(scope="session")
+def synth():
+    import kmsr_b200.synth as s
+    return s
+
+
+@pytest.fixture(scope="session")
+def bank(golden):
+    z = golden("moe_bank.npz")
+    return z["kernels"], z["sigmas"]
