@@ -1,0 +1,184 @@
+/*
+ * kmsr.h -- C ABI of libkmsr.so: the B200 (sm_100a) LR/HR pair-synthesis hot path.
+ *
+ * The reference (Zhiyyeah/Kernel-Modeling-Super-Resolution) has no FFI: its boundary for this
+ * path is a set of Python functions that call torch/numpy on the CPU.  Each entry point below
+ * replaces the arithmetic of one of those call sites; the Python drop-ins in
+ * kernel-modeling-super-resolution_b200/ keep the reference signatures and bind these symbols
+ * with ctypes (INTEGRATION.md shows the stub).  Paths are relative to
+ * /root/reference/kernel_from_lr_gan/.
+ *
+ * Conventions
+ *   - every pointer named below is a DEVICE pointer unless it says "host";
+ *   - the caller (PyTorch's allocator) owns every buffer, outputs and workspaces included:
+ *     the library never allocates or frees device memory and keeps no pointer after a call;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     stream-ordered and asynchronous with respect to the host;
+ *   - return value 0 = success, negative = KMSR_E_*; the message of the last failure on the
+ *     calling thread is available from kmsr_last_error().  Nothing throws, nothing exits;
+ *   - float32 CHW images, band order 443/490/555/660/865 nm (C_30apply_kernel_to_landsat.py:49).
+ */
+#ifndef KMSR_H_
+#define KMSR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define KMSR_API
+#else
+#define KMSR_API __attribute__((visibility("default")))
+#endif
+
+#define KMSR_VERSION 100 /* 0.1.0 */
+
+enum {
+    KMSR_OK = 0,
+    KMSR_E_INVALID = -1,     /* bad argument (shape, mode, null pointer) */
+    KMSR_E_UNSUPPORTED = -2, /* valid request this build has no kernel for */
+    KMSR_E_CUDA = -3,        /* CUDA runtime / driver error (message has the cudaError string) */
+    KMSR_E_ALIGN = -4        /* pointer or stride not aligned as the chosen kernel requires */
+};
+
+/* pad_mode: how the blur sees pixels outside the patch */
+enum {
+    KMSR_PAD_REPLICATE = 0, /* F.pad(mode='replicate')  C_30:107-109, C_31:85-87 */
+    KMSR_PAD_ZERO = 1       /* F.conv2d(padding=k//2)   muti_kernel/train_gemini.py:128 */
+};
+/* down_mode: how the blurred image is reduced */
+enum {
+    KMSR_DOWN_BOXMEAN = 0, /* int(log2(f)) cascaded avg_pool2d(2,2)  C_30:120-122, C_31:92-95 */
+    KMSR_DOWN_DECIMATE = 1 /* out[:, :, ::f, ::f]                     muti_kernel/train_gemini.py:134 */
+};
+/* noise_mode: what is added to the degraded patch */
+enum {
+    KMSR_NOISE_NONE = 0,  /* C_30 / C_31 output ('blurred' / 'lr' group) */
+    KMSR_NOISE_ADD = 1,   /* blurred + noise_pool[idx]                E_make_train_data.py:72-74 */
+    KMSR_NOISE_SIGMA = 2  /* blurred + sigma[kidx,c] * noise          muti_kernel/train_gemini.py:137 */
+};
+/* algo: kernel selection for kmsr_degrade_* */
+enum {
+    KMSR_ALGO_AUTO = 0,    /* TMA row-streaming kernel when the shape qualifies, else the tiled kernel */
+    KMSR_ALGO_TILED = 1,   /* generic polyphase shared-memory tile kernel (any k, factor, H, W)      */
+    KMSR_ALGO_TMA = 2      /* TMA row-streaming kernel; KMSR_E_UNSUPPORTED if the shape does not qualify */
+};
+
+/* ---- library ------------------------------------------------------------------------------- */
+KMSR_API int kmsr_version(void);
+KMSR_API const char* kmsr_last_error(void);
+/* Device facts used to size grids / report rooflines (cudaGetDeviceProperties). */
+KMSR_API int kmsr_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
+                              int64_t* l2_bytes, int64_t* smem_optin_bytes);
+
+/* ---- a2/a3: blur + downsample (+ noise) ------------------------------------------------------
+ * Replaces apply_kernel_degradation (C_30:68-124 == C_31:59-97) for a batch of patches, the
+ * multi-kernel + sigma composition of SURVEY.md 8a row 3 (train_gemini.py:107-138) and the
+ * fused E.add_noise (E_make_train_data.py:65-74).
+ *
+ * Shape helpers (host only, no device work):
+ *   effective factor f' = 2^floor(log2(factor))      (C_30:121  int(np.log2(f)))
+ *   blurred size  Hb = H + 2*(kh/2) - kh + 1         (C_30:107-117; H for odd kh, H+1 for even)
+ *   BOXMEAN : Ho = Hb / f' (floor, equals the cascaded floors), composite window KH = kh + f' - 1,
+ *             stride f'
+ *   DECIMATE: Ho = ceil(Hb / factor), composite window = kernel, stride = factor
+ */
+KMSR_API int kmsr_degrade_out_size(int H, int W, int kh, int kw, int factor, int down_mode,
+                                   int* Ho, int* Wo);
+KMSR_API int kmsr_composite_size(int kh, int kw, int factor, int down_mode,
+                                 int* KH, int* KW, int* stride);
+/* bytes of the `workspace` kmsr_degrade_batch needs (composite bank + per-band sum residuals) */
+KMSR_API int64_t kmsr_degrade_workspace_bytes(int64_t nK, int C, int kh, int kw, int factor,
+                                              int down_mode);
+
+/* Normalise every band of every kernel as C_30:93-97 does (divide by the band sum iff it is > 0),
+ * fold the box mean into it (composite stride-f' kernel) and record
+ * dsum[k,c] = sum(normalised band) - 1.
+ *   kbank [nK, C, kh, kw]  ->  comp [nK, C, KH, KW],  dsum [nK, C]                              */
+KMSR_API int kmsr_prepare_kernels(const float* kbank, int64_t nK, int C, int kh, int kw,
+                                  int factor, int down_mode, float* comp, float* dsum,
+                                  void* stream);
+
+/* lr[n,c] = degrade(hr[n], K[kidx[n]])[c]  (+ scale[n,c] * pool[nidx[n], c])
+ *   hr            patch n band c row y starts at hr + off(n) + c*hr_stride_c + y*hr_stride_h
+ *                 (element strides; rows contiguous); off(n) = patch_offsets ? patch_offsets[n]
+ *                 : n*hr_stride_n.  patch_offsets lets patches be overlapping views of a scene
+ *                 (A_00_patch_cutter_universal.py:176).
+ *   comp, dsum    from kmsr_prepare_kernels (same kh, kw, factor, down_mode)
+ *   kidx  [N]     kernel per patch, NULL = kernel 0 for all (C_30 / C_31 single-kernel apply)
+ *   sigma [nK,C]  only for KMSR_NOISE_SIGMA
+ *   pool  [nPool, C, Ho, Wo], nidx [N]   only when noise_mode != NONE
+ *   lr    [N, C, Ho, Wo] contiguous
+ */
+KMSR_API int kmsr_degrade_prepared(const float* hr, int64_t N, int C, int H, int W,
+                                   int64_t hr_stride_n, int64_t hr_stride_c, int64_t hr_stride_h,
+                                   const int64_t* patch_offsets,
+                                   const float* comp, const float* dsum, int64_t nK, int kh, int kw,
+                                   const int32_t* kidx,
+                                   const float* sigma, const float* pool, int64_t nPool,
+                                   const int32_t* nidx,
+                                   int factor, int pad_mode, int down_mode, int noise_mode,
+                                   float* lr, int algo, void* stream);
+
+/* kmsr_prepare_kernels into `workspace`, then kmsr_degrade_prepared, on the same stream. */
+KMSR_API int kmsr_degrade_batch(const float* hr, int64_t N, int C, int H, int W,
+                                int64_t hr_stride_n, int64_t hr_stride_c, int64_t hr_stride_h,
+                                const int64_t* patch_offsets,
+                                const float* kbank, int64_t nK, int kh, int kw,
+                                const int32_t* kidx,
+                                const float* sigma, const float* pool, int64_t nPool,
+                                const int32_t* nidx,
+                                int factor, int pad_mode, int down_mode, int noise_mode,
+                                float* lr, void* workspace, int64_t workspace_bytes,
+                                int algo, void* stream);
+
+/* ---- a5: noise-pool gather + add (E_make_train_data.py:65-74) -------------------------------
+ * out[n] = blurred[n] + scale * pool[nidx[n]],  scale = 1 (sigma NULL) or sigma[kidx[n], c].
+ * blurred/out [N, C, hw], pool [nPool, C, hw]; indices are drawn on the host (bit-exact MT19937). */
+KMSR_API int kmsr_add_noise(const float* blurred, int64_t N, int C, int64_t hw,
+                            const float* pool, int64_t nPool, const int32_t* nidx,
+                            const float* sigma, const int32_t* kidx, float* out, void* stream);
+
+/* ---- a4: noise-pool construction (D_build_noise_pool.py:88 + :41-53) ------------------------
+ * pool[m, c, y, x] = geo[c, top[m]+y, left[m]+x] - den[c, top[m]+y, left[m]+x]  for one file;
+ * top/left [n_samples] are host-drawn (CPython random.randint, inclusive bounds).             */
+KMSR_API int kmsr_crop_sub(const float* geo, const float* den, int C, int H, int W,
+                           const int32_t* top, const int32_t* left, int64_t n_samples, int crop,
+                           float* pool, void* stream);
+
+/* ---- a7: per-band statistics (data_mean_std.py:32-33, 45-46) --------------------------------
+ * For every patch n and band c: NaN-skipping mean and population std over hw pixels.
+ *   x [N, C, hw] (patch stride x_stride_n elements, bands contiguous)
+ *   mean, std [N, C] float64 (per patch, what np.nanmean / np.nanstd return before S:41-46)
+ *   sums [2*C + 1] float64, ACCUMULATED (+=): sum over patches of mean[c], of std[c], and N --
+ *        the 88-byte vector the multi-GPU path all-reduces.  May be NULL.        */
+KMSR_API int kmsr_band_stats(const float* x, int64_t N, int C, int64_t hw, int64_t x_stride_n,
+                             double* mean, double* std, double* sums, void* stream);
+
+/* ---- a8: scene mask + patch keep-mask (A_00_patch_cutter_universal.py:89-123, 152-183) ------
+ * kmsr_water_mask: data [C, hw] is updated IN PLACE (invalid -> NaN, CUT:102) and masked [C, hw]
+ * receives NaN wherever NIR (band nir) is outside [tmin, tmax] or NaN (CUT:108-113).
+ * `masked` may alias `data`.                                                                   */
+KMSR_API int kmsr_water_mask(float* data, int C, int64_t hw, int nir, float invalid,
+                             float tmin, float tmax, float* masked, void* stream);
+/* keep[i, j] = 1 iff the P x P window at (i*stride, j*stride) over all C bands holds no more than
+ * nan_threshold * C*P*P NaNs (CUT:179-183; 0.0 = none).  nan_count [hp, wp] int32 optional.
+ * workspace: kmsr_keep_mask_workspace_bytes(H, W, P, stride).                                   */
+KMSR_API int64_t kmsr_keep_mask_workspace_bytes(int H, int W, int P, int stride);
+KMSR_API int kmsr_keep_mask(const float* masked, int C, int H, int W, int P, int stride,
+                            double nan_threshold, uint8_t* keep, int32_t* nan_count,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------
+ * Launch counter: number of kernels this library launched on the calling process since load.   */
+KMSR_API int64_t kmsr_launch_count(void);
+/* Name of the kernel the last kmsr_degrade_* call on this thread selected ("tiled" | "tma"). */
+KMSR_API const char* kmsr_last_algo(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMSR_H_ */

@@ -1,0 +1,122 @@
+// stats.cu -- per-band NaN-skipping mean / population std (data_mean_std.py:32-33) and the
+// deterministic sum over patches that S:45-46 (np.mean over patches) and the multi-GPU
+// all-reduce consume.
+//
+// One CTA per (patch, band).  True two-pass like numpy: pass 1 accumulates sum(x - p) with
+// p = first pixel (fp32 per thread, fp64 across threads), pass 2 re-reads the band (L2 hit: a
+// band is 256 KB) and accumulates (x - mean)^2 with the mean split into hi + lo floats.
+#include "common.cuh"
+
+namespace kmsr {
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; ++i) t += red[i];     // fixed order: deterministic
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+band_stats_kernel(const float* __restrict__ x, int C, long long hw, long long stride_n,
+                  double* __restrict__ mean, double* __restrict__ stdv) {
+    __shared__ double red[8];
+    const long long band = blockIdx.x;
+    const long long n = band / C;
+    const int c = (int)(band % C);
+    const float* p = x + n * stride_n + (long long)c * hw;
+    const bool vec = (hw % 4 == 0) && (((uintptr_t)p & 15) == 0);
+
+    float pv = p[0];
+    if (!isfinite(pv)) pv = 0.0f;
+
+    float s = 0.0f;
+    unsigned cnt = 0;
+    if (vec) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+        for (long long i = threadIdx.x; i < (hw >> 2); i += blockDim.x) {
+            const float4 v = p4[i];
+            if (v.x == v.x) { s += v.x - pv; ++cnt; }
+            if (v.y == v.y) { s += v.y - pv; ++cnt; }
+            if (v.z == v.z) { s += v.z - pv; ++cnt; }
+            if (v.w == v.w) { s += v.w - pv; ++cnt; }
+        }
+    } else {
+        for (long long i = threadIdx.x; i < hw; i += blockDim.x) {
+            const float v = p[i];
+            if (v == v) { s += v - pv; ++cnt; }
+        }
+    }
+    const double S1 = block_sum((double)s, red);
+    const double Nn = block_sum((double)cnt, red);
+    const double m = Nn > 0.0 ? (double)pv + S1 / Nn : nan("");
+    const float mh = (float)m;
+    const float ml = (float)(m - (double)mh);
+
+    float q = 0.0f;
+    if (vec) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+        for (long long i = threadIdx.x; i < (hw >> 2); i += blockDim.x) {
+            const float4 v = p4[i];
+            float d;
+            if (v.x == v.x) { d = (v.x - mh) - ml; q = fmaf(d, d, q); }
+            if (v.y == v.y) { d = (v.y - mh) - ml; q = fmaf(d, d, q); }
+            if (v.z == v.z) { d = (v.z - mh) - ml; q = fmaf(d, d, q); }
+            if (v.w == v.w) { d = (v.w - mh) - ml; q = fmaf(d, d, q); }
+        }
+    } else {
+        for (long long i = threadIdx.x; i < hw; i += blockDim.x) {
+            const float v = p[i];
+            if (v == v) { const float d = (v - mh) - ml; q = fmaf(d, d, q); }
+        }
+    }
+    const double S2 = block_sum((double)q, red);
+    if (threadIdx.x == 0) {
+        mean[band] = m;
+        stdv[band] = Nn > 0.0 ? sqrt(S2 / Nn) : nan("");
+    }
+}
+
+// sums[c] += sum_n mean[n,c]; sums[C+c] += sum_n std[n,c]; sums[2C] += N.  One CTA per output,
+// strided partials then a fixed-order tree: bitwise reproducible for a given N.
+__global__ void __launch_bounds__(256)
+stats_reduce_kernel(const double* __restrict__ mean, const double* __restrict__ stdv, long long N,
+                    int C, double* __restrict__ sums) {
+    __shared__ double red[256];
+    const int o = blockIdx.x;
+    if (o == 2 * C) {
+        if (threadIdx.x == 0) sums[o] += (double)N;
+        return;
+    }
+    const double* src = o < C ? mean + o : stdv + (o - C);
+    double s = 0.0;
+    for (long long n = threadIdx.x; n < N; n += blockDim.x) s += src[n * C];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[o] += red[0];
+}
+
+int launch_band_stats(const float* x, long long N, int C, long long hw, long long stride_n,
+                      double* mean, double* stdv, double* sums, cudaStream_t st) {
+    if (N == 0) return KMSR_OK;
+    KMSR_REQUIRE(N * C < (1ll << 31), KMSR_E_INVALID, "band_stats: N*C too large");
+    KMSR_REQUIRE(hw > 0, KMSR_E_INVALID, "band_stats: empty bands");
+    band_stats_kernel<<<(unsigned)(N * C), 256, 0, st>>>(x, C, hw, stride_n, mean, stdv);
+    KMSR_LAUNCH_CHECK("band_stats_kernel");
+    if (sums) {
+        stats_reduce_kernel<<<2 * C + 1, 256, 0, st>>>(mean, stdv, N, C, sums);
+        KMSR_LAUNCH_CHECK("stats_reduce_kernel");
+    }
+    return KMSR_OK;
+}
+
+}  // namespace kmsr

@@ -1,0 +1,235 @@
+"""Batched device entry points: thin tensor-level wrappers over the C ABI (include/kmsr.h).
+
+PyTorch supplies device memory and the current stream; every flop happens in libkmsr's CUDA
+kernels.  All tensors are float32 CHW (reference layout, C_30apply_kernel_to_landsat.py:59-60);
+indices are int32 and are drawn on the host (rng.py) so they match the reference bit for bit.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("kmsr_b200 computes on a CUDA device (B200, sm_100a); none is visible and "
+                           "there is no CPU fallback")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.float32)
+
+
+def _i32(t, device) -> torch.Tensor | None:
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t))
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+@dataclass
+class PreparedBank:
+    """Normalised + box-folded kernel bank on the device (kmsr_prepare_kernels)."""
+    comp: torch.Tensor      # [nK, C, KH, KWp]
+    dsum: torch.Tensor      # [nK, C]
+    nK: int
+    C: int
+    kh: int
+    kw: int
+    factor: int
+    down_mode: int
+
+
+def prepare_kernels(kbank: torch.Tensor, factor: int = 8, down_mode: str | int = "boxmean") -> PreparedBank:
+    """kbank [nK, C, kh, kw] (or [C, kh, kw]) -> PreparedBank.  C_30:93-97 normalisation + box fold."""
+    require_cuda()
+    dm = L.DOWN_MODES[down_mode] if isinstance(down_mode, str) else int(down_mode)
+    if kbank.ndim == 3:
+        kbank = kbank.unsqueeze(0)
+    if kbank.ndim != 4:
+        raise ValueError(f"kernel bank must be [nK,C,kh,kw] or [C,kh,kw], got {tuple(kbank.shape)}")
+    dev = kbank.device if kbank.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    kb = _f32(kbank, dev).contiguous()
+    nK, Cb, kh, kw = kb.shape
+    KH, KWp, _ = L.composite_size(kh, kw, factor, dm)
+    comp = torch.empty((nK, Cb, KH, KWp), dtype=torch.float32, device=dev)
+    dsum = torch.empty((nK, Cb), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().kmsr_prepare_kernels(_ptr(kb), nK, Cb, kh, kw, factor, dm, _ptr(comp), _ptr(dsum),
+                                             _stream(dev)))
+    return PreparedBank(comp, dsum, nK, Cb, kh, kw, int(factor), dm)
+
+
+def degrade_batch(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, nidx=None,
+                  factor: int = 8, pad_mode: str = "replicate", down_mode: str = "boxmean",
+                  noise_mode: str | None = None, out: torch.Tensor | None = None, algo: str = "auto",
+                  patch_offsets: torch.Tensor | None = None, patch_hw: tuple[int, int] | None = None,
+                  strides: tuple[int, int, int] | None = None, n_patches: int | None = None) -> torch.Tensor:
+    """lr[n,c] = degrade(hr[n], K[kidx[n]])[c] (+ scale * pool[nidx[n], c]) on the device.
+
+    hr: CUDA float32 [N, C, H, W] with contiguous rows (any N / C / row strides), or -- with
+    `patch_offsets` (int64 element offsets), `patch_hw`, `strides=(sC, sH)` -- a base tensor that the
+    patches are windows of (scene-scale path, A_00_patch_cutter_universal.py:176).
+    kbank: tensor [nK,C,kh,kw] / [C,kh,kw] or a PreparedBank.
+    """
+    require_cuda()
+    if not hr.is_cuda or hr.dtype != torch.float32:
+        raise TypeError("degrade_batch expects a CUDA float32 tensor (drop-in wrappers copy host inputs)")
+    dev = hr.device
+    dm = L.DOWN_MODES[down_mode]
+    pm = L.PAD_MODES[pad_mode]
+    if noise_mode is None:
+        noise_mode = "none" if nidx is None else ("sigma" if sigma is not None else "add")
+    nm = L.NOISE_MODES[noise_mode]
+    bank = kbank if isinstance(kbank, PreparedBank) else prepare_kernels(kbank.to(dev), factor, dm)
+    if bank.factor != factor or bank.down_mode != dm:
+        raise ValueError("PreparedBank was built for a different factor / down_mode")
+
+    if patch_offsets is None:
+        if hr.ndim != 4:
+            raise ValueError(f"hr must be [N,C,H,W], got {tuple(hr.shape)}")
+        N, Cc, H, W = hr.shape
+        if hr.stride(3) != 1 and W > 1:
+            hr = hr.contiguous()
+        sN, sC, sH = hr.stride(0), hr.stride(1), hr.stride(2)
+        po = None
+    else:
+        Cc = bank.C
+        H, W = patch_hw
+        sC, sH = strides
+        sN = 0
+        po = patch_offsets.to(device=dev, dtype=torch.int64).contiguous()
+        N = int(po.numel()) if n_patches is None else int(n_patches)
+    assert Cc == bank.C, f"kernel bands ({bank.C}) != image bands ({Cc})"      # C_30:88
+    Ho, Wo = L.degrade_out_size(H, W, bank.kh, bank.kw, factor, dm)
+    if out is None:
+        out = torch.empty((N, Cc, Ho, Wo), dtype=torch.float32, device=dev)
+    else:
+        assert out.is_cuda and out.is_contiguous() and tuple(out.shape) == (N, Cc, Ho, Wo)
+    kidx_d = _i32(kidx, dev)
+    nidx_d = _i32(nidx, dev)
+    sig = None if sigma is None else _f32(torch.as_tensor(sigma), dev).contiguous()
+    pl = None
+    npool = 0
+    if nm != L.NOISE_NONE:
+        if pool is None or nidx_d is None:
+            raise ValueError("noise requested without pool / nidx")
+        pl = pool if (pool.is_cuda and pool.dtype == torch.float32 and pool.is_contiguous()) \
+            else _f32(pool, dev).contiguous()
+        npool = pl.shape[0]
+        if tuple(pl.shape[1:]) != (Cc, Ho, Wo):
+            raise ValueError(f"noise pool {tuple(pl.shape)} does not match LR patches {(Cc, Ho, Wo)}")
+    with torch.cuda.device(dev):
+        L.check(L.lib().kmsr_degrade_prepared(
+            _ptr(hr), N, Cc, H, W, sN, sC, sH, _ptr(po),
+            _ptr(bank.comp), _ptr(bank.dsum), bank.nK, bank.kh, bank.kw, _ptr(kidx_d),
+            _ptr(sig), _ptr(pl), npool, _ptr(nidx_d),
+            factor, pm, dm, nm, _ptr(out), L.ALGOS[algo], _stream(dev)))
+    return out
+
+
+def add_noise_batch(blurred: torch.Tensor, pool: torch.Tensor, nidx, *, sigma=None, kidx=None,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
+    """out[n] = blurred[n] + scale * pool[nidx[n]]  (E_make_train_data.py:72-74; scale 1 unless sigma)."""
+    require_cuda()
+    dev = blurred.device
+    b = blurred.contiguous()
+    N, Cc = b.shape[0], b.shape[1]
+    hw = int(np.prod(b.shape[2:]))
+    pl = pool if pool.is_cuda else pool.to(dev)
+    pl = pl.contiguous()
+    if tuple(pl.shape[1:]) != tuple(b.shape[1:]):
+        raise ValueError(f"noise pool {tuple(pl.shape)} does not match patches {tuple(b.shape)}")
+    if out is None:
+        out = torch.empty_like(b)
+    sig = None if sigma is None else _f32(torch.as_tensor(sigma), dev).contiguous()
+    with torch.cuda.device(dev):
+        L.check(L.lib().kmsr_add_noise(_ptr(b), N, Cc, hw, _ptr(pl), pl.shape[0], _ptr(_i32(nidx, dev)),
+                                       _ptr(sig), _ptr(_i32(kidx, dev)), _ptr(out), _stream(dev)))
+    return out
+
+
+def crop_sub(geo: torch.Tensor, den: torch.Tensor, top, left, crop: int) -> torch.Tensor:
+    """pool[m] = (geo - den)[:, top[m]:top[m]+crop, left[m]:left[m]+crop]  (D_build_noise_pool.py:88, :51)."""
+    require_cuda()
+    dev = geo.device
+    g = geo.contiguous()
+    d = den.to(dev).contiguous()
+    Cc, H, W = g.shape
+    t = _i32(np.asarray(top), dev)
+    l = _i32(np.asarray(left), dev)
+    n = int(t.numel())
+    out = torch.empty((n, Cc, crop, crop), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().kmsr_crop_sub(_ptr(g), _ptr(d), Cc, H, W, _ptr(t), _ptr(l), n, crop, _ptr(out),
+                                      _stream(dev)))
+    return out
+
+
+def band_stats(x: torch.Tensor, sums: torch.Tensor | None = None):
+    """Per-patch per-band NaN-skipping mean / population std (data_mean_std.py:32-33).
+
+    x [N, C, ...] CUDA float32 -> (mean [N,C] f64, std [N,C] f64).  `sums` (f64 [2C+1], device) is
+    accumulated in place: sum of means, sum of stds, patch count -- the vector the ranks all-reduce.
+    """
+    require_cuda()
+    dev = x.device
+    N, Cc = x.shape[0], x.shape[1]
+    hw = int(np.prod(x.shape[2:]))
+    flat = x.reshape(N, Cc, hw)
+    if flat.stride(2) != 1 or flat.stride(1) != hw:
+        flat = flat.contiguous()
+    mean = torch.empty((N, Cc), dtype=torch.float64, device=dev)
+    std = torch.empty((N, Cc), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().kmsr_band_stats(_ptr(flat), N, Cc, hw, flat.stride(0) if N > 1 else Cc * hw,
+                                        _ptr(mean), _ptr(std), _ptr(sums), _stream(dev)))
+    return mean, std
+
+
+def water_mask(data: torch.Tensor, tmin: float, tmax: float, nir: int = 4, invalid: float = -9999.0,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """In place invalid->NaN on `data`, returns the masked copy (A_00_patch_cutter_universal.py:102-113)."""
+    require_cuda()
+    assert data.is_cuda and data.is_contiguous() and data.dtype == torch.float32
+    Cc = data.shape[0]
+    hw = int(np.prod(data.shape[1:]))
+    if out is None:
+        out = torch.empty_like(data)
+    with torch.cuda.device(data.device):
+        L.check(L.lib().kmsr_water_mask(_ptr(data), Cc, hw, nir, invalid, tmin, tmax, _ptr(out),
+                                        _stream(data.device)))
+    return out
+
+
+def keep_mask(masked: torch.Tensor, patch_size: int = 256, stride: int = 128, nan_threshold: float = 0.0):
+    """keep[i,j] / NaN count of every window (A_00_patch_cutter_universal.py:152-183)."""
+    require_cuda()
+    assert masked.is_cuda and masked.is_contiguous() and masked.dtype == torch.float32
+    dev = masked.device
+    Cc, H, W = masked.shape
+    hp = (H - patch_size) // stride + 1 if H >= patch_size else 0
+    wp = (W - patch_size) // stride + 1 if W >= patch_size else 0
+    keep = torch.zeros((max(hp, 0), max(wp, 0)), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros((max(hp, 0), max(wp, 0)), dtype=torch.int32, device=dev)
+    if hp > 0 and wp > 0:
+        wsb = int(L.lib().kmsr_keep_mask_workspace_bytes(H, W, patch_size, stride))
+        ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.lib().kmsr_keep_mask(_ptr(masked), Cc, H, W, patch_size, stride, float(nan_threshold),
+                                           _ptr(keep), _ptr(cnt), _ptr(ws), wsb, _stream(dev)))
+    return keep.bool(), cnt

@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing: one process per GPU, patches sharded in contiguous ranges, no data-path
+collective; the only exchange is the (2C+1)-double sum of per-patch statistics.
+
+Every rank draws ALL host indices from the single seeded stream and slices its range, so the
+outputs are bit-identical for any world size.  Works over NCCL (device tensors) and gloo (CPU
+tensors, used by the CPU tests).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import rng
+
+
+@dataclass
+class ShardPlan:
+    n: int
+    rank: int
+    world: int
+
+    @property
+    def start(self) -> int:
+        return rng.shard_range(self.n, self.rank, self.world)[0]
+
+    @property
+    def stop(self) -> int:
+        return rng.shard_range(self.n, self.rank, self.world)[1]
+
+    @property
+    def count(self) -> int:
+        return self.stop - self.start
+
+    def take(self, arr):
+        return arr[self.start:self.stop]
+
+
+def env_rank_world() -> tuple[int, int, int]:
+    """(rank, local_rank, world) from the torchrun environment; (0, 0, 1) when absent."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise torch.distributed from the torchrun environment (no-op for a single process)."""
+    import torch.distributed as dist
+    rank, local, world = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+def local_stat_sums(mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
+    """[N,C] per-patch means / stds of this rank -> f64 [2C+1] = (sum mean, sum std, N)."""
+    c = mean.shape[1]
+    out = torch.zeros(2 * c + 1, dtype=torch.float64, device=mean.device)
+    out[:c] = mean.to(torch.float64).sum(dim=0)
+    out[c:2 * c] = std.to(torch.float64).sum(dim=0)
+    out[2 * c] = mean.shape[0]
+    return out
+
+
+def allreduce_stat_sums(sums: torch.Tensor) -> torch.Tensor:
+    """SUM all-reduce of the 2C+1 doubles (88 bytes at C=5) when a process group exists."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    return sums
+
+
+def finish_stats(sums: torch.Tensor):
+    """(avg_mean [C], avg_std [C], count): data_mean_std.py:45-46 over all ranks' patches."""
+    s = sums.detach().cpu().numpy()
+    c = (s.shape[0] - 1) // 2
+    n = s[2 * c]
+    return s[:c] / n, s[c:2 * c] / n, int(round(n))

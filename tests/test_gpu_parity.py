@@ -1,0 +1,335 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libkmsr.so) against the oracle and against
+the golden vectors produced by the real reference (tests/golden/make_golden.py).
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8c):
+  * LR pixels: max|d| <= 1e-5 x (band max - band min) of the HR patch band;
+  * indices, offsets, gathers, adds, masks: bit exact;
+  * statistics: <= 1e-6 relative to fp64 truth.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kmsr_oracle as orc
+from oracle import oracle_c
+
+pytestmark = pytest.mark.gpu
+
+PIX_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def K():
+    import kmsr_b200
+    from kmsr_b200 import _lib, ops, rng
+    from kmsr_b200 import C_30apply_kernel_to_landsat as C30
+    from kmsr_b200 import C_31apply_muti_kernel_to_landsat as C31
+    from kmsr_b200 import D_build_noise_pool as D
+    from kmsr_b200 import E_make_train_data as E
+    from kmsr_b200 import data_mean_std as S
+    from kmsr_b200 import A_00_patch_cutter_universal as CUT
+
+    class NS:
+        pass
+    ns = NS()
+    ns.lib, ns.ops, ns.rng, ns.C30, ns.C31, ns.D, ns.E, ns.S, ns.CUT = _lib, ops, rng, C30, C31, D, E, S, CUT
+    assert torch.cuda.is_available()
+    return ns
+
+
+def _case_inputs(z, name, synth):
+    if f"{name}__img" in z.files:
+        img = z[f"{name}__img"]
+    else:
+        img = synth.make_hr(1, int(z[f"{name}__seed"]), "textured")[0]
+        assert hashlib.sha256(img.tobytes()).hexdigest() == str(z[f"{name}__sha256"])
+    return img, z[f"{name}__kernel"], int(z[f"{name}__factor"])
+
+
+@pytest.mark.parametrize("algo", ["tiled", "auto"])
+def test_golden_degrade_cases(K, golden, synth, algo):
+    """Every reference-generated case (edge shapes, odd dims, 2-D kernels, zero taps, unnormalised and
+    non-positive-sum kernels, k=11/21, factors 1/2/4/6/8, 3 bands, water stress case)."""
+    z = golden("golden_degrade.npz")
+    worst = {}
+    for name in z["cases"]:
+        img, kern, f = _case_inputs(z, name, synth)
+        ref = z[f"{name}__out"]
+        k = torch.from_numpy(kern)
+        if k.ndim == 2:
+            k = k.unsqueeze(0).repeat(img.shape[0], 1, 1)
+        out = K.ops.degrade_batch(torch.from_numpy(img).cuda().unsqueeze(0), k.cuda(), factor=f,
+                                  algo=algo)[0].cpu().numpy()
+        assert out.shape == ref.shape, name
+        worst[name] = orc.rel_err(out, ref, orc.band_range(img))
+    bad = {k: v for k, v in worst.items() if not v <= PIX_TOL}
+    assert not bad, (bad, worst)
+
+
+def test_dropin_signatures_match_reference_outputs(K, golden, synth):
+    """C_30 / C_31 apply_kernel_degradation with CPU tensors in, CPU tensors out."""
+    z = golden("golden_degrade.npz")
+    for name in ("p64_k13_s8", "p64_kernel2d", "p256_water", "odd_70x52_s8", "c3_bands"):
+        img, kern, f = _case_inputs(z, name, synth)
+        for mod in (K.C30, K.C31):
+            out = mod.apply_kernel_degradation(torch.from_numpy(img), torch.from_numpy(kern), f)
+            assert isinstance(out, torch.Tensor) and not out.is_cuda and out.dtype == torch.float32
+            assert orc.rel_err(out.numpy(), z[f"{name}__out"], orc.band_range(img)) <= PIX_TOL, name
+    img, kern, _ = _case_inputs(z, "p64_k13_s8", synth)
+    out = K.C30.apply_kernel_degradation(torch.from_numpy(img).cuda(), torch.from_numpy(kern).cuda())
+    assert out.is_cuda and out.shape == (5, 8, 8)                       # default factor 8
+
+
+def test_config1_single_kernel_64_patches(K, synth, bank):
+    """BASELINE config 1: kernel_0 on 64 synthetic 256x256 patches, all 64 checked against the oracle."""
+    kb, _ = bank
+    hr = np.concatenate([synth.make_hr(32, 1235, "textured"), synth.make_hr(32, 1236, "water")])
+    lr = K.C30.degrade_patches(torch.from_numpy(hr), torch.from_numpy(kb[0]), 8).numpy()
+    assert lr.shape == (64, 5, 32, 32)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = np.stack([orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kb[0]), 8).numpy()
+                    for i in range(64)])
+    err = np.abs(lr.astype(np.float64) - ref) / orc.band_range(hr)
+    assert err.max() <= PIX_TOL, err.reshape(64, -1).max(axis=1)
+
+
+@pytest.mark.parametrize("algo", ["tiled", "auto"])
+def test_config2_multi_kernel_sigma_noise(K, synth, bank, golden, algo):
+    """BASELINE config 2 composition on a 192-patch subset: indices exact, pixels within tolerance."""
+    kb, sb = bank
+    n = 192
+    g = golden("golden_rng.npz")
+    kidx, nidx = K.rng.draw_multi_kernel_indices(4096, 10, 4096, 42)
+    assert np.array_equal(kidx, g["cfg2_kidx"]) and np.array_equal(nidx, g["cfg2_nidx"])
+    kidx, nidx = kidx[:n], nidx[:n]
+    pool = synth.make_noise_pool(4096, 42)
+    hr = np.concatenate([synth.make_hr(n // 2, 1236, "textured"), synth.make_hr(n // 2, 1237, "water")])
+    lr = K.ops.degrade_batch(torch.from_numpy(hr).cuda(), torch.from_numpy(kb).cuda(), kidx=kidx,
+                             sigma=torch.from_numpy(sb), pool=torch.from_numpy(pool).cuda(), nidx=nidx,
+                             factor=8, noise_mode="sigma", algo=algo).cpu().numpy()
+    ref = orc.multi_kernel_pairs(hr, kb, sb, pool, kidx, nidx, 8)
+    err = np.abs(lr.astype(np.float64) - ref) / orc.band_range(hr)
+    assert err.max() <= PIX_TOL, err.reshape(n, -1).max(axis=1)
+    # noise really is sigma-scaled pool noise: removing it leaves the plain degrade
+    plain = K.ops.degrade_batch(torch.from_numpy(hr).cuda(), torch.from_numpy(kb).cuda(), kidx=kidx,
+                                factor=8, algo=algo).cpu().numpy()
+    nz = sb[kidx][:, :, None, None].astype(np.float64) * pool[nidx]
+    assert np.abs((lr - plain) - nz).max() <= 2e-5
+
+
+def test_e_pair_assembly_matches_reference_chain(K, synth, bank):
+    """C_30 -> E.add_noise chain fused in one launch: same indices as E's global stream, scale-1 add."""
+    kb, _ = bank
+    n = 24
+    hr = synth.make_hr(n, 1240, "textured")
+    pool = synth.make_noise_pool(512, 42)
+    _, lr, nidx = K.E.make_pairs(hr, kb[3], pool, seed=42)
+    assert np.array_equal(nidx, orc.draw_noise_indices(n, 512, 42))
+    blurred = [orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kb[3]), 8).numpy() for i in range(n)]
+    pairs = orc.make_pairs(list(hr), blurred, pool, seed=42)
+    ref = np.stack([p[1] for p in pairs])
+    assert orc.rel_err(lr.numpy(), ref, orc.band_range(hr)) <= PIX_TOL
+
+
+def test_gem_mode_zero_pad_decimate(K, synth, bank):
+    """train_gemini.py:124-134 variant: zero padding + [::4] decimation, per-sample kernels."""
+    kb, _ = bank
+    hr = synth.make_hr(6, 1250, "textured", size=128)
+    kidx = np.array([0, 3, 9, 1, 7, 7], dtype=np.int32)
+    lr = K.ops.degrade_batch(torch.from_numpy(hr).cuda(), torch.from_numpy(kb).cuda(), kidx=kidx, factor=4,
+                             pad_mode="zero", down_mode="decimate").cpu().numpy()
+    ref = orc.multi_kernel_pairs(hr, kb, None, None, kidx, None, 4, "zero", "decimate", "none")
+    assert lr.shape == ref.shape == (6, 5, 32, 32)
+    assert orc.rel_err(lr, ref, orc.band_range(hr)) <= PIX_TOL
+
+
+def test_add_noise_bit_exact(K, golden, synth):
+    z = golden("golden_rng.npz")
+    pool = synth.make_noise_pool(64, int(z["pool64_seed"]))
+    np.random.seed(42)
+    for b, want in zip(z["add_noise_blurred"], z["add_noise_out"]):
+        got = K.E.add_noise(b, pool)                              # consumes the global numpy stream
+        assert got.dtype == np.float32 and np.array_equal(got, want)
+    # batched gather + sigma scaling equals the fp32 fma of the oracle's C restatement
+    idx = np.array([5, 0, 63], dtype=np.int32)
+    sig = np.array([[0.75, 0.8, 0.85, 0.9, 0.95]], dtype=np.float32)
+    out = K.ops.add_noise_batch(torch.from_numpy(z["add_noise_blurred"]).cuda(), torch.from_numpy(pool).cuda(),
+                                idx, sigma=sig).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(out[i], oracle_c.add_noise(z["add_noise_blurred"][i], pool[idx[i]], sig[0]))
+
+
+def test_noise_pool_bit_exact(K, golden):
+    z = golden("golden_noise_pool.npz")
+    shapes = [tuple(s) for s in z["shapes"]]
+    geos = [z[f"geo{i}"] for i in range(len(shapes))]
+    dens = [z[f"den{i}"] for i in range(len(shapes))]
+    pool, offs = K.D.build_noise_pool_arrays(geos, dens, 2, 32, 42, return_offsets=True)
+    assert np.array_equal(offs, z["offsets"])
+    assert pool.dtype == np.float32 and np.array_equal(pool, z["pool"])
+    import random
+    random.seed(42)
+    crops = K.D.random_crop(geos[0] - dens[0], 32, 2)
+    assert all(np.array_equal(c, w) for c, w in zip(crops, z["pool"][:2]))
+    with pytest.raises(ValueError):
+        K.D.random_crop(np.zeros((5, 16, 64), np.float32), 32, 1)
+
+
+def test_band_stats(K, golden, synth, capsys):
+    z = golden("golden_stats.npz")
+    patches = z["patches"]
+    r = K.S.radiance_stats(patches)
+    m64, s64, am, asd = orc.radiance_stats_f64(patches)
+    assert np.allclose(r["mean"], m64, rtol=1e-6, atol=0) and np.allclose(r["std"], s64, rtol=1e-6, atol=0)
+    assert np.allclose(r["avg_mean"], am, rtol=1e-6) and np.allclose(r["avg_std"], asd, rtol=1e-6)
+    big = np.concatenate([synth.make_hr(4, 5, "textured"), synth.make_hr(4, 6, "water")])
+    big[2, 1, 100:140, 17] = np.nan
+    big[5, 4] = np.nan                                           # a fully-NaN band -> NaN mean/std
+    r = K.S.radiance_stats(big)
+    m64, s64, _, _ = orc.radiance_stats_f64(big)
+    ok = ~np.isnan(m64)
+    assert np.array_equal(np.isnan(r["mean"]), ~ok) and np.array_equal(np.isnan(r["std"]), ~ok)
+    assert np.allclose(r["mean"][ok], m64[ok], rtol=1e-6) and np.allclose(r["std"][ok], s64[ok], rtol=1e-6)
+
+
+def test_analyze_radiance_stats_printout(K, golden, tmp_path, capsys):
+    """The drop-in prints the same table numbers as the reference did on the same files (S:48-62)."""
+    import re
+    z = golden("golden_stats.npz")
+    for i, p in enumerate(z["patches"]):
+        np.save(tmp_path / f"patch_{i:03d}.npy", p)
+    assert K.S.analyze_radiance_stats(str(tmp_path), int(z["num_samples"])) is None
+    got = capsys.readouterr().out
+    pat = r"Band (\d)\s*\|\s*([-\d.eE+nan]+)\s*\|\s*([-\d.eE+nan]+)"
+    want_rows = re.findall(pat, str(z["stdout"]))
+    got_rows = re.findall(pat, got)
+    assert len(got_rows) == len(want_rows) == 5
+    for a, b in zip(got_rows, want_rows):
+        assert abs(float(a[1]) - float(b[1])) <= 1e-4 * abs(float(b[1])) + 1e-6
+        assert abs(float(a[2]) - float(b[2])) <= 1e-4 * abs(float(b[2])) + 1e-6
+
+
+def test_water_mask_and_tiling(K, golden, synth):
+    z = golden("golden_cutter.npz")
+    scene = synth.make_scene(int(z["scene_seed"]), *z["scene_shape"][1:], n_fill=3, n_cloud=3)
+    data = scene.copy()
+    masked = K.CUT.apply_water_mask(data, K.CUT.THRESHOLD_MIN, K.CUT.THRESHOLD_MAX)
+    assert np.array_equal(np.packbits(np.isnan(masked)), z["masked_nan"])
+    assert np.array_equal(np.packbits(np.isnan(data)), z["inplace_nan"])
+    assert hashlib.sha256(np.nan_to_num(masked, nan=-1.0).tobytes()).hexdigest() == str(z["masked_sha256"])
+    total, kept, ij, offsets, dev_scene = K.CUT.create_patches(masked, 256, 0.5, 0.0)
+    assert total == int(z["total"]) and kept == int(z["kept"])
+    assert np.array_equal(ij, z["kept_ij"][:, :2])
+    # kept windows, read back through their offsets, are the reference's patches byte for byte
+    w = masked.shape[2]
+    flat = dev_scene.reshape(5, -1)
+    for (i, j), off, h16 in zip(ij, offsets.tolist(), z["kept_patch_sha16"]):
+        assert off == i * 128 * w + j * 128
+        p = dev_scene[:, i * 128:i * 128 + 256, j * 128:j * 128 + 256].contiguous().cpu().numpy()
+        assert hashlib.sha256(p.tobytes()).hexdigest()[:16] == str(h16)
+    # general thresholds and a stride that does not divide the patch (direct kernel)
+    keep, cnt = K.ops.keep_mask(torch.from_numpy(masked).cuda(), 96, 40, 0.02)
+    ref = orc.keep_mask(masked, 96, 40 / 96, 0.02)
+    assert np.array_equal(keep.cpu().numpy(), ref)
+    keep, cnt = K.ops.keep_mask(torch.from_numpy(masked).cuda(), 128, 64, 0.3)
+    assert np.array_equal(keep.cpu().numpy(), orc.keep_mask(masked, 128, 0.5, 0.3))
+
+
+def test_scene_windows_degrade_like_cut_patches(K, golden, synth, bank):
+    """Config 4 path: degrading kept windows in place (patch_offsets) == degrading the cut patches;
+    the replicate halo clamps to the WINDOW, not to the scene."""
+    kb, _ = bank
+    z = golden("golden_cutter.npz")
+    scene = synth.make_scene(int(z["scene_seed"]), *z["scene_shape"][1:], n_fill=3, n_cloud=3)
+    masked = orc.apply_water_mask(scene.copy(), 1e-6, 7.0)
+    total, kept, ij, offsets, dev_scene = K.CUT.create_patches(masked, 256, 0.5, 0.0)
+    assert kept > 0
+    h, w = masked.shape[1:]
+    for algo in ("tiled", "auto"):
+        lr = K.ops.degrade_batch(dev_scene, torch.from_numpy(kb[2]).cuda(), factor=8, patch_offsets=offsets,
+                                 patch_hw=(256, 256), strides=(h * w, w), algo=algo).cpu().numpy()
+        for n, (i, j) in enumerate(ij[:6]):
+            p = masked[:, i * 128:i * 128 + 256, j * 128:j * 128 + 256]
+            ref = orc.apply_kernel_degradation(torch.from_numpy(np.ascontiguousarray(p)), torch.from_numpy(kb[2]), 8).numpy()
+            assert orc.rel_err(lr[n], ref, orc.band_range(p)) <= PIX_TOL
+
+
+def test_nan_propagation_matches_reference(K, synth, bank):
+    """A NaN pixel poisons exactly the LR pixels whose (clamped) window contains it."""
+    kb, _ = bank
+    hr = synth.make_hr(2, 1260, "textured")
+    hr[0, 1, 0, 0] = np.nan            # corner: replicated into the halo
+    hr[0, 3, 130, 77] = np.nan
+    hr[1, 0, 255, 200] = np.nan
+    for algo in ("tiled", "auto"):
+        lr = K.ops.degrade_batch(torch.from_numpy(hr).cuda(), torch.from_numpy(kb[0]).cuda(), factor=8,
+                                 algo=algo).cpu().numpy()
+        for i in range(2):
+            ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kb[0]), 8).numpy()
+            assert np.array_equal(np.isnan(lr[i]), np.isnan(ref)), algo
+            ok = ~np.isnan(ref)
+            rng_ = np.broadcast_to(orc.band_range(hr[i]), ref.shape)
+            assert (np.abs(lr[i][ok] - ref[ok]) / rng_[ok]).max() <= PIX_TOL
+
+
+def test_full_size_properties(K, synth, bank):
+    """BASELINE config 2 size (4096 patches) through size-independent properties:
+    shard invariance (bitwise), constant patches stay constant, additivity of the noise term."""
+    kb, sb = bank
+    n = 4096
+    base = torch.from_numpy(synth.make_hr(64, 1270, "textured")).cuda()
+    hr = base.repeat(n // 64, 1, 1, 1)
+    hr += torch.arange(n, device="cuda", dtype=torch.float32).view(n, 1, 1, 1) * 0.01   # distinct patches
+    pool = torch.from_numpy(synth.make_noise_pool(4096, 42)).cuda()
+    kidx, nidx = K.rng.draw_multi_kernel_indices(n, 10, 4096, 42)
+    kbd = torch.from_numpy(kb).cuda()
+    full = K.ops.degrade_batch(hr, kbd, kidx=kidx, sigma=torch.from_numpy(sb), pool=pool, nidx=nidx, factor=8)
+    assert full.shape == (n, 5, 32, 32) and bool(torch.isfinite(full).all())
+    for world in (2, 8):
+        parts = []
+        for r in range(world):
+            a, b = K.rng.shard_range(n, r, world)
+            parts.append(K.ops.degrade_batch(hr[a:b], kbd, kidx=kidx[a:b], sigma=torch.from_numpy(sb), pool=pool,
+                                             nidx=nidx[a:b], factor=8))
+        assert torch.equal(torch.cat(parts), full), f"shards differ at world={world}"
+    # the tiled and the TMA kernels agree to well inside the tolerance on every patch
+    tiled = K.ops.degrade_batch(hr, kbd, kidx=kidx, sigma=torch.from_numpy(sb), pool=pool, nidx=nidx, factor=8,
+                                algo="tiled")
+    rngs = (hr.amax(dim=(2, 3)) - hr.amin(dim=(2, 3)))[:, :, None, None]
+    assert float(((tiled - full).abs() / rngs).max()) <= PIX_TOL
+    # constant patch -> constant output (normalised kernels sum to one)
+    const = torch.full((16, 5, 256, 256), 37.25, device="cuda")
+    out = K.ops.degrade_batch(const, kbd, kidx=np.arange(16, dtype=np.int32) % 10, factor=8)
+    assert float((out - 37.25).abs().max()) <= 37.25 * 4e-7
+    # checksum of checksums: per-band LR mean equals HR band mean up to boundary weighting
+    plain = K.ops.degrade_batch(hr[:256], kbd, kidx=kidx[:256], factor=8)
+    assert float((plain.mean(dim=(2, 3)) - hr[:256].mean(dim=(2, 3))).abs().max()) < 0.5
+
+
+def test_c_abi_error_codes(K):
+    """Bad arguments come back as negative codes with a message; nothing throws inside the library."""
+    import ctypes as C
+    lib = K.lib.lib()
+    x = torch.zeros(1, 5, 64, 64, device="cuda")
+    comp = torch.zeros(1, 5, 20, 20, device="cuda")
+    ds = torch.zeros(1, 5, device="cuda")
+    out = torch.zeros(1, 5, 8, 8, device="cuda")
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.kmsr_degrade_prepared(vp(x), 1, 5, 64, 64, 5 * 4096, 4096, 64, None, vp(comp), vp(ds), 1, 13, 13,
+                                   None, None, None, 0, None, 8, 7, 0, 0, vp(out), 0, None)
+    assert rc == K.lib.E_INVALID and "pad_mode" in K.lib.last_error()
+    rc = lib.kmsr_degrade_prepared(vp(x), 1, 5, 64, 64, 5 * 4096, 4096, 64, None, vp(comp), vp(ds), 1, 13, 13,
+                                   None, None, None, 0, None, 8, 0, 0, 1, vp(out), 0, None)
+    assert rc == K.lib.E_INVALID and "noise" in K.lib.last_error()
+    rc = lib.kmsr_degrade_prepared(vp(x), 1, 5, 64, 64, 5 * 4096, 4096, 64, None, vp(comp), vp(ds), 1, 13, 13,
+                                   None, None, None, 0, None, 8, 0, 0, 0, vp(out), K.lib.ALGO_TMA, None)
+    assert rc == K.lib.E_UNSUPPORTED
+    rc = lib.kmsr_crop_sub(vp(x), vp(x), 5, 16, 64, None, None, 1, 32, vp(out), None)
+    assert rc == K.lib.E_INVALID and "smaller than crop" in K.lib.last_error()
+    with pytest.raises(K.lib.KmsrError):
+        K.lib.check(rc)
+    # empty batch is a no-op success
+    assert lib.kmsr_degrade_prepared(None, 0, 5, 64, 64, 0, 0, 64, None, None, None, 1, 13, 13, None, None, None,
+                                     0, None, 8, 0, 0, 0, None, 0, None) == 0

@@ -1,0 +1,198 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports what include/kmsr.h declares,
+shape algebra, host index draws against the reference's golden streams, the drop-ins' argument
+contracts (exception types of the reference), loud failure without a device, and the world_size-2
+sharding + statistics all-reduce over gloo.  No compute entry point is called here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    import __graft_entry__ as g
+    from kmsr_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        g.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(L):
+    hdr = open(os.path.join(ROOT, "include", "kmsr.h")).read()
+    declared = set(re.findall(r"KMSR_API\s+[\w\s\*]+?\b(kmsr_\w+)\s*\(", hdr))
+    assert len(declared) >= 17
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    lib = L.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.kmsr_version() == 100
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (kmsr_\w+)", out))
+    assert declared <= exported
+    # nothing but the C ABI is exported, and the library does not depend on torch
+    assert not [s for s in re.findall(r"\b[TW] (\w+)", out) if not s.startswith("kmsr_")]
+    ldd = subprocess.run(["ldd", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "c10" not in ldd
+
+
+def test_shape_algebra_matches_reference_rules(L, golden):
+    # effective factor 2**int(log2(f)) (C_30:121), floors at each pooling stage, even kernels give H+1 rows
+    assert L.degrade_out_size(256, 256, 13, 13, 8) == (32, 32)
+    assert L.degrade_out_size(256, 256, 13, 13, 6) == (64, 64)
+    assert L.degrade_out_size(70, 52, 13, 13, 8) == (8, 6)
+    assert L.degrade_out_size(64, 64, 13, 13, 1) == (64, 64)
+    assert L.degrade_out_size(64, 64, 12, 12, 2) == (32, 32)          # blurred 65 -> 32
+    assert L.degrade_out_size(128, 128, 13, 13, 4, L.DOWN_DECIMATE) == (32, 32)
+    assert L.degrade_out_size(130, 130, 13, 13, 4, L.DOWN_DECIMATE) == (33, 33)
+    assert L.composite_size(13, 13, 8) == (20, 20, 8)
+    assert L.composite_size(13, 13, 6) == (16, 16, 4)
+    assert L.composite_size(11, 11, 4, L.DOWN_DECIMATE) == (11, 12, 4)  # pitch padded to 4 floats
+    z = golden("golden_degrade.npz")
+    for name in z["cases"]:
+        k = z[f"{name}__kernel"]
+        img_shape = z[f"{name}__img"].shape if f"{name}__img" in z.files else (5, 256, 256)
+        ho, wo = L.degrade_out_size(img_shape[1], img_shape[2], k.shape[-2], k.shape[-1], int(z[f"{name}__factor"]))
+        assert (ho, wo) == z[f"{name}__out"].shape[1:], name
+    with pytest.raises(L.KmsrError):
+        L.degrade_out_size(64, 64, 0, 13, 8)
+    assert L.lib().kmsr_degrade_workspace_bytes(10, 5, 13, 13, 8, 0) >= 10 * 5 * 400 * 4
+
+
+def test_host_index_streams_bit_exact(golden):
+    from kmsr_b200 import rng
+    z = golden("golden_rng.npz")
+    assert np.array_equal(rng.draw_noise_indices(256, 4096, 42), z["e_idx_seed42_pool4096_n256"])
+    assert np.array_equal(rng.draw_noise_indices(64, 1000, 7), z["e_idx_seed7_pool1000_n64"])
+    assert np.array_equal(rng.draw_noise_indices(8, 1, 5), z["e_idx_seed5_pool1_n8"])
+    # continuing the global stream without reseeding, as successive E.add_noise calls do
+    a = rng.draw_noise_indices(100, 4096, 42)
+    b = rng.draw_noise_indices(156, 4096, None)
+    assert np.array_equal(np.concatenate([a, b]), z["e_idx_seed42_pool4096_n256"])
+    kidx, nidx = rng.draw_multi_kernel_indices(4096, 10, 4096, 42)
+    assert kidx.dtype == np.int32 and np.array_equal(kidx, z["cfg2_kidx"]) and np.array_equal(nidx, z["cfg2_nidx"])
+    d = golden("golden_noise_pool.npz")
+    import random
+    random.seed(42)
+    offs = []
+    for (h, w) in d["shapes"]:
+        t, l = rng.draw_crop_offsets(int(h), int(w), 32, 2)
+        offs.extend(zip(t, l))
+    assert np.array_equal(np.array(offs), d["offsets"])
+    random.seed(42)
+    t, l = rng.draw_crop_offsets(256, 300, 32, 200)
+    assert np.array_equal(np.stack([t, l], 1), d["offsets_seed42_256x300_n200"])
+    with pytest.raises(ValueError):
+        rng.draw_crop_offsets(16, 64, 32, 1)
+    with pytest.raises(ValueError):
+        rng.draw_noise_indices(3, 0, 1)
+
+
+def test_shard_ranges_partition_exactly():
+    from kmsr_b200 import rng
+    for n in (0, 1, 7, 64, 4096, 100000):
+        for g in (1, 2, 3, 4, 8):
+            r = [rng.shard_range(n, k, g) for k in range(g)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(g - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_dropin_argument_contracts(golden):
+    """Exception types of the reference (golden 'error_types'), raised before any device work."""
+    from kmsr_b200 import C_30apply_kernel_to_landsat as C30, C_31apply_muti_kernel_to_landsat as C31
+    z = golden("golden_degrade.npz")
+    want = {":".join(s.split(":")[:2]): s.split(":")[2] for s in z["error_types"]}
+    img = torch.zeros(5, 64, 64)
+    for mod, tag in ((C30, "c30"), (C31, "c31")):
+        with pytest.raises(AssertionError):
+            mod.apply_kernel_degradation(img, torch.zeros(4, 13, 13), 8)
+        assert want[f"{tag}:bands4"] == "AssertionError"
+    with pytest.raises(ValueError):
+        C31.apply_kernel_degradation(img, torch.zeros(1, 5, 13, 13), 8)
+    assert want["c31:ndim4"] == "ValueError"
+    with pytest.raises(Exception) as ei:
+        C30.apply_kernel_degradation(img, torch.zeros(1, 5, 13, 13), 8)
+    assert type(ei.value).__name__ == want["c30:ndim4"]
+
+
+def test_load_kernel_forms(golden, tmp_path, capsys):
+    from kmsr_b200 import C_30apply_kernel_to_landsat as C30, C_31apply_muti_kernel_to_landsat as C31
+    z = golden("golden_load_kernel.npz")
+    for name in ("k3", "k2", "k4"):
+        p = tmp_path / f"{name}.npy"
+        np.save(p, z[f"{name}_in"])
+        assert np.array_equal(C30.load_kernel(str(p)).numpy(), z[f"{name}_c30"])
+        assert np.array_equal(C31.load_kernel(str(p)).numpy(), z[f"{name}_c31"])
+    assert "shape" in capsys.readouterr().out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_compute_entry_points_fail_loudly_without_a_device(bank):
+    from kmsr_b200 import C_30apply_kernel_to_landsat as C30, E_make_train_data as E, data_mean_std as S
+    kb, _ = bank
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        C30.apply_kernel_degradation(torch.zeros(5, 64, 64), torch.from_numpy(kb[0]), 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        E.add_noise(np.zeros((5, 32, 32), np.float32), np.zeros((4, 5, 32, 32), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        S.radiance_stats(np.zeros((2, 5, 8, 8), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "kernel-modeling-super-resolution_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from kmsr_b200 import rng, shard
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+n, c = 37, 5
+rs = np.random.RandomState(3)
+means = rs.rand(n, c); stds = rs.rand(n, c)
+# every rank draws ALL indices from the single seeded stream, then slices its shard
+kidx, nidx = rng.draw_multi_kernel_indices(n, 10, 4096, 42)
+a, b = rng.shard_range(n, rank, world)
+plan = shard.ShardPlan(n, rank, world)
+assert (plan.start, plan.stop) == (a, b)
+local = shard.local_stat_sums(torch.from_numpy(means[a:b]), torch.from_numpy(stds[a:b]))
+tot = shard.allreduce_stat_sums(local)
+am, asd, cnt = shard.finish_stats(tot)
+assert cnt == n
+assert np.allclose(am, means.mean(0), rtol=1e-12) and np.allclose(asd, stds.mean(0), rtol=1e-12)
+gathered = [None] * world
+dist.all_gather_object(gathered, (kidx[a:b].tolist(), nidx[a:b].tolist()))
+if rank == 0:
+    assert sum((g[0] for g in gathered), []) == kidx.tolist()
+    assert sum((g[1] for g in gathered), []) == nidx.tolist()
+    print("OK")
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo_sharding_and_stats_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29500 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "OK" in outs[0]
