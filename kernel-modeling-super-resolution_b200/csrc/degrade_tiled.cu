@@ -76,24 +76,46 @@ degrade_tiled_kernel(const TiledParams p) {
 
     for (int i = threadIdx.x; i < p.KH * p.KWp; i += 256) wts[i] = __ldg(kc + i);
 
-    // stage the window: warps over rows, lanes over columns (coalesced global reads)
+    // stage the window: warps over row pairs, lanes over columns (coalesced global reads).  The loads
+    // of a 2 x 256 element slab are all issued before the first store so that 16 requests per thread
+    // are in flight (one-at-a-time loads left the kernel latency-bound at 3 % of HBM bandwidth).
     const bool zero_pad = p.pad_mode == KMSR_PAD_ZERO;
-    for (int r = warp; r < p.IR; r += 8) {
-        const int gy = oy0 * S + r - p.pt;
-        const bool yin = gy >= 0 && gy < p.H;
-        const float* row = img + (long long)min(max(gy, 0), p.H - 1) * p.sH;
-        float* trow = tile + r * p.RP;
-        for (int cc = lane; cc < p.ICp; cc += 32) {
-            const int gx = ox0 * S + cc - p.pl;
-            const bool xin = gx >= 0 && gx < p.W;
-            float v = 0.0f;
-            if (cc < p.IC) {
-                if (!zero_pad || (yin && xin)) v = __ldg(row + min(max(gx, 0), p.W - 1)) - pv;
-                else v = -pv;                       // a zero-padded pixel, pivot-shifted
+    for (int r0 = warp * 2; r0 < p.IR; r0 += 16) {
+        for (int cc0 = 0; cc0 < p.ICp; cc0 += 256) {
+            float v[2][8];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = r0 + rr;
+                const int gy = oy0 * S + r - p.pt;
+                const bool yin = gy >= 0 && gy < p.H;
+                const float* row = img + (long long)min(max(gy, 0), p.H - 1) * p.sH;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int cc = cc0 + lane + 32 * j;
+                    const int gx = ox0 * S + cc - p.pl;
+                    const bool xin = gx >= 0 && gx < p.W;
+                    float t = 0.0f;
+                    if (r < p.IR && cc < p.IC) {
+                        if (!zero_pad || (yin && xin)) t = __ldg(row + min(max(gx, 0), p.W - 1)) - pv;
+                        else t = -pv;                   // a zero-padded pixel, pivot-shifted
+                    }
+                    v[rr][j] = t;
+                }
             }
-            int t, m;
-            split_col<S_>(cc, S, t, m);
-            trow[t * p.PM + m] = v;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int r = r0 + rr;
+                if (r >= p.IR) continue;
+                float* trow = tile + r * p.RP;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int cc = cc0 + lane + 32 * j;
+                    if (cc >= p.ICp) continue;
+                    int t, m;
+                    split_col<S_>(cc, S, t, m);
+                    trow[t * p.PM + m] = v[rr][j];
+                }
+            }
         }
     }
     __syncthreads();
