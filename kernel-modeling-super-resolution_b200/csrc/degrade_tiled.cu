@@ -211,7 +211,7 @@ int launch_degrade_tiled(const DegradeArgs& a, cudaStream_t st) {
     const int M = (p.ICp + S - 1) / S;
     // words per phase plane: M rounded so that the staging stores of 32 adjacent columns
     // (S phases x 32/S words) fall in 32 different banks when S divides 32, odd otherwise
-    if (S <= 32 && 32 % S == 0) p.PM = ((M + 31) / 32) * 32 + (S == 1 ? 0 : 32 / S);
+    if (S <= 32 && 32 % S == 0) p.PM = M + (((32 / S) % 32 - M) % 32 + 32) % 32;     // smallest >= M, == 32/S (mod 32)
     else p.PM = M | 1;
     p.RP = S * p.PM;
 

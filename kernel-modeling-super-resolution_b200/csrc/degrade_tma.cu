@@ -9,14 +9,16 @@
 //    256 x 256 band top to bottom in chunks of 8 rows; every HR byte crosses HBM -> SMEM exactly
 //    once (no vertical halo re-read) through a ring of TMA tiles (cp.async.bulk.tensor, one
 //    producer thread, full/empty mbarriers).  The tensor map describes [N, C, H, W/2] 64-bit
-//    elements and the box is 138 x 8 starting at x = -3: TMA's out-of-bounds zero fill lays each
-//    row down as [6 halo | 256 pixels | 14 pad] with a pitch of 276 floats = 69 x 16 B (odd), so
-//    a quarter-warp reading the same 16-byte column of 8 consecutive rows is bank-conflict free.
+//    elements and the box is 138 x 8 starting at x = -4 (the byte offset of a box start must be a
+//    multiple of 16: x = -3 raises an illegal-instruction fault, measured): TMA's out-of-bounds
+//    zero fill lays each row down as [8 halo | 256 pixels | 12 pad] with a pitch of 276 floats =
+//    69 x 16 B (odd), so a quarter-warp reading the same 16-byte column of 8 consecutive rows is
+//    bank-conflict free.
 //  * two warps per stream; lane = (ly, gx): ly = row residue mod 8, gx = group of 4 adjacent LR
 //    columns.  A lane owns input rows r == ly (mod 8) and keeps the 2-3 composite-kernel rows that
 //    can meet such a row (u = ly, ly+8, ly+16) in REGISTERS for the whole band: 60 weights, no
 //    shared-memory weight traffic.  Per 8-row chunk a lane loads its 44-float row segment once
-//    (11 LDS.128) and feeds 200 useful FMAs from it (3 output rows x 4 output columns x 20 taps).
+//    (12 LDS.128) and feeds 200 useful FMAs from it (3 output rows x 4 output columns x 20 taps).
 //  * replicate padding never touches shared memory: rows clamp by address, the six halo columns of
 //    the two edge groups are substituted in registers.
 //  * the 8 row-residue partial sums of an output are combined with a 4-shuffle reduce-scatter and
@@ -43,6 +45,9 @@ constexpr int kChunkBytes = kChunkF * 4;       // 8832 = 69 * 128
 constexpr int kConsumerWarps = 2 * kStreams;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kSegF = 3 * kS + kKW;            // 44 floats: the row segment 4 adjacent outputs need
+constexpr int kLeftF = 8;                      // staged halo columns left of pixel 0 (16-byte aligned box start)
+constexpr int kSkew = kLeftF - kPad;           // 2: the segment starts 2 floats into its first 16-byte chunk
+constexpr int kLoadF = (kSkew + kSegF + 3) / 4 * 4;   // 48 floats = 12 LDS.128
 constexpr size_t kSmemBytes = (size_t)kStreams * kDepth * kChunkBytes + 2 * kStreams * kDepth * 8 + 128;
 
 struct TmaArgs {
@@ -134,7 +139,7 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
                 mbar_arrive_expect_tx(full0 + 8 * b, kChunkBytes);
                 const long long n = band[s] / a.C;
                 const int c = (int)(band[s] - n * a.C);
-                tma_load_4d(smem_u32(ring + (size_t)b * kChunkF), &tmap, -(kPad / 2), kS * chunk[s] - kPad, c,
+                tma_load_4d(smem_u32(ring + (size_t)b * kChunkF), &tmap, -(kLeftF / 2), kS * chunk[s] - kPad, c,
                             (int)n, full0 + 8 * b);
                 if (++slot[s] == kDepth) { slot[s] = 0; par[s] ^= 1; }
                 if (++chunk[s] == a.nchunks) { chunk[s] = 0; band[s] += G; }
@@ -204,18 +209,21 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
             const int r = min(max(kS * i + ly - kPad, 0), a.H - 1);          // replicate: clamp by address
             const float* src = sring + (size_t)slot * kChunkF + (r + kPad - kS * ci) * kRowF + 32 * g;
             if (i == 0) {
-                pv = sring[(size_t)slot * kChunkF + kPad * kRowF + 32 * g + kPad];   // pixel (0, 32g)
+                pv = sring[(size_t)slot * kChunkF + kPad * kRowF + 32 * g + kLeftF];   // pixel (0, 32g)
                 if (!isfinite(pv)) pv = 0.0f;
             }
-            float d[kSegF];
+            float e[kLoadF];
 #pragma unroll
-            for (int j = 0; j < kSegF / 4; ++j) {
+            for (int j = 0; j < kLoadF / 4; ++j) {
                 const float4 t = reinterpret_cast<const float4*>(src)[j];
-                d[4 * j + 0] = t.x; d[4 * j + 1] = t.y; d[4 * j + 2] = t.z; d[4 * j + 3] = t.w;
+                e[4 * j + 0] = t.x; e[4 * j + 1] = t.y; e[4 * j + 2] = t.z; e[4 * j + 3] = t.w;
             }
+            float d[kSegF];                    // d[j] = pixel column 32g - 6 + j
+#pragma unroll
+            for (int j = 0; j < kSegF; ++j) d[j] = e[j + kSkew];
             // this chunk is no longer needed once its rows sit in registers -- except the last one,
             // which the bottom-halo step reads again
-            const bool release = (i != a.nchunks - 1);
+            const bool release = i < a.nchunks - 1;
             __syncwarp();
             if (release && lane == 0) mbar_arrive(sempty + 8 * slot);
             if (release) { if (++slot == kDepth) { slot = 0; par ^= 1; } }
@@ -322,7 +330,7 @@ int launch_degrade_tma(const DegradeArgs& a, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
     KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "degrade (tma): cuTensorMapEncodeTiled is not available from the driver");
     CUtensorMap tmap;
-    // [N, C, H, W/2] of 64-bit elements; box = 138 x 8 x 1 x 1 (x starts at -3: zero-filled halo)
+    // [N, C, H, W/2] of 64-bit elements; box = 138 x 8 x 1 x 1 (x starts at -4: zero-filled halo)
     cuuint64_t gdim[4] = {(cuuint64_t)(a.W / 2), (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.N};
     const long long sN = a.N > 1 ? a.sN : (long long)a.C * a.sC;
     cuuint64_t gstr[3] = {(cuuint64_t)a.sH * 4, (cuuint64_t)a.sC * 4, (cuuint64_t)sN * 4};
