@@ -134,7 +134,8 @@ def test_e_pair_assembly_matches_reference_chain(K, synth, bank):
     blurred = [orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kb[3]), 8).numpy() for i in range(n)]
     pairs = orc.make_pairs(list(hr), blurred, pool, seed=42)
     ref = np.stack([p[1] for p in pairs])
-    assert orc.rel_err(lr.numpy(), ref, orc.band_range(hr)) <= PIX_TOL
+    for i in range(n):
+        check_pixels(lr[i].numpy(), ref[i], hr[i], name=f"pair{i}")       # textured regime: the pure bar
 
 
 def test_gem_mode_zero_pad_decimate(K, synth, bank):
@@ -146,7 +147,8 @@ def test_gem_mode_zero_pad_decimate(K, synth, bank):
                              pad_mode="zero", down_mode="decimate").cpu().numpy()
     ref = orc.multi_kernel_pairs(hr, kb, None, None, kidx, None, 4, "zero", "decimate", "none")
     assert lr.shape == ref.shape == (6, 5, 32, 32)
-    assert orc.rel_err(lr, ref, orc.band_range(hr)) <= PIX_TOL
+    for i in range(6):
+        check_pixels(lr[i], ref[i], hr[i], name=f"gem{i}")
 
 
 def test_add_noise_bit_exact(K, golden, synth):
@@ -257,7 +259,7 @@ def test_scene_windows_degrade_like_cut_patches(K, golden, synth, bank):
         for n, (i, j) in enumerate(ij[:6]):
             p = masked[:, i * 128:i * 128 + 256, j * 128:j * 128 + 256]
             ref = orc.apply_kernel_degradation(torch.from_numpy(np.ascontiguousarray(p)), torch.from_numpy(kb[2]), 8).numpy()
-            assert orc.rel_err(lr[n], ref, orc.band_range(p)) <= PIX_TOL
+            check_pixels(lr[n], ref, p, exact_degrade(np.ascontiguousarray(p), kb[2], 8), name=f"window{n}")
 
 
 def test_nan_propagation_matches_reference(K, synth, bank):
