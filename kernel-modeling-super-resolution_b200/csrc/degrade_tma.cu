@@ -5,12 +5,13 @@
 // folded into a 20 x 20 stride-8 composite kernel, E_make_train_data.py:72-74 /
 // train_gemini.py:137 noise in the epilogue); what changes is how the bytes move:
 //
-//  * persistent CTAs (two per SM), each running 2 independent band streams.  A stream walks a
+//  * persistent CTAs (one per SM), each running 4 independent band streams.  A stream walks a
 //    256 x 256 band top to bottom in chunks of 8 rows; every HR byte crosses HBM -> SMEM exactly
 //    once (no vertical halo re-read) through a ring of TMA tiles (cp.async.bulk.tensor, one
-//    producer thread per CTA, full/empty mbarriers).  One producer thread sustains one 8.8 KB
-//    request per ~280 ns, i.e. 4.3 TB/s chip-wide with one CTA per SM (scratch/feed_probe.cu);
-//    two producers per SM lift the feed to 6.5 TB/s, which is why the CTA is half an SM.  The tensor map describes [N, C, H, W/2] 64-bit
+//    producer thread per STREAM, full/empty mbarriers).  One producer thread sustains one 8.8 KB
+//    request per ~280 ns, i.e. 4.3 TB/s chip-wide with one producer per SM (scratch/feed_probe.cu);
+//    a producer warp per stream lifts the feed to the chip's read ceiling and spreads the 12 warps
+//    evenly over the four schedulers (2 consumers + 1 sleeping producer each).  The tensor map describes [N, C, H, W/2] 64-bit
 //    elements and the box is 138 x 8 starting at x = -4 (the byte offset of a box start must be a
 //    multiple of 16: x = -3 raises an illegal-instruction fault, measured): TMA's out-of-bounds
 //    zero fill lays each row down as [8 halo | 256 pixels | 12 pad] with a pitch of 276 floats =
@@ -44,14 +45,15 @@ constexpr int kS = 8;                          // output stride (effective downs
 constexpr int kK = 13;                         // blur kernel size
 constexpr int kKW = kK + kS - 1;               // 20: composite window
 constexpr int kPad = kK / 2;                   // 6
-constexpr int kStreams = 2;                    // band streams per CTA
-constexpr int kCtasPerSm = 2;
+constexpr int kStreams = 4;                    // band streams per CTA
+constexpr int kCtasPerSm = 1;
 constexpr int kDepth = 5;                      // ring slots per stream
 constexpr int kRowF = 276;                     // floats per staged row (138 x 8 B box)
 constexpr int kChunkF = 8 * kRowF;             // floats per chunk
 constexpr int kChunkBytes = kChunkF * 4;       // 8832 = 69 * 128
 constexpr int kConsumerWarps = 2 * kStreams;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kProducerWarps = kStreams;        // one producer warp (one thread) per stream
+constexpr int kThreads = (kConsumerWarps + kProducerWarps) * 32;
 constexpr int kSegF = 3 * kS + kKW;            // 44 floats: the row segment 4 adjacent outputs need
 constexpr int kLeftF = 8;                      // staged halo columns left of pixel 0 (16-byte aligned box start)
 constexpr int kSkew = kLeftF - kPad;           // 2: the segment starts 2 floats into its first 16-byte chunk
@@ -172,35 +174,28 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
     const long long Gn = G / a.C;
     const int Gc = (int)(G - Gn * a.C);
 
-    if (warp == kConsumerWarps) {
-        // ===================== TMA producer: one thread feeds the rings =====================
+    if (warp >= kConsumerWarps) {
+        // ============ TMA producers: warp kConsumerWarps + s, lane 0, feeds the ring of stream s ============
+        // (12 warps = 3 per scheduler: two consumers and one mostly-sleeping producer each, so the FMA pipes
+        // of the four schedulers carry the same load)
         if (lane != 0 || MODE == 2) return;
-        long long band[kStreams], pn[kStreams];
-        int pc[kStreams], chunk[kStreams], slot[kStreams];
-        uint32_t par[kStreams];
-#pragma unroll
-        for (int s = 0; s < kStreams; ++s) {
-            band[s] = (long long)blockIdx.x * kStreams + s;
-            pn[s] = band[s] / a.C; pc[s] = (int)(band[s] - pn[s] * a.C);
-            chunk[s] = 0; slot[s] = 0; par[s] = 1;       // fresh barriers: waiting on parity 1 passes
-        }
-        bool active = true;
-        while (active) {
-            active = false;
-#pragma unroll
-            for (int s = 0; s < kStreams; ++s) {
-                if (band[s] >= a.nbands) continue;
-                active = true;
-                const int b = s * kDepth + slot[s];
-                mbar_wait(empty0 + 8 * b, par[s]);
-                mbar_arrive_expect_tx(full0 + 8 * b, kChunkBytes);
-                tma_load_4d(smem_u32(ring + (size_t)b * kChunkF), &tmap, -(kLeftF / 2), kS * chunk[s] - kPad, pc[s],
-                            (int)pn[s], full0 + 8 * b);
-                if (++slot[s] == kDepth) { slot[s] = 0; par[s] ^= 1; }
-                if (++chunk[s] == a.nchunks) {
-                    chunk[s] = 0; band[s] += G; pn[s] += Gn; pc[s] += Gc;
-                    if (pc[s] >= a.C) { pc[s] -= a.C; ++pn[s]; }
-                }
+        const int s = warp - kConsumerWarps;
+        long long band = (long long)blockIdx.x * kStreams + s;
+        long long pn = band / a.C;
+        int pc = (int)(band - pn * a.C);
+        int chunk = 0, slot = 0;
+        uint32_t par = 1;                                // fresh barriers: waiting on parity 1 passes
+        const uint32_t sfull = full0 + 8 * s * kDepth, sempty = empty0 + 8 * s * kDepth;
+        float* sring = ring + (size_t)s * kDepth * kChunkF;
+        while (band < a.nbands) {
+            mbar_wait(sempty + 8 * slot, par);
+            mbar_arrive_expect_tx(sfull + 8 * slot, kChunkBytes);
+            tma_load_4d(smem_u32(sring + (size_t)slot * kChunkF), &tmap, -(kLeftF / 2), kS * chunk - kPad, pc, (int)pn,
+                        sfull + 8 * slot);
+            if (++slot == kDepth) { slot = 0; par ^= 1; }
+            if (++chunk == a.nchunks) {
+                chunk = 0; band += G; pn += Gn; pc += Gc;
+                if (pc >= a.C) { pc -= a.C; ++pn; }
             }
         }
         return;
@@ -409,11 +404,91 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
             }
         };
 
+        // Interior steps (3 <= i <= Ho-1) need none of the step lambda's case analysis: the chunk is fresh
+        // and released, rows are unclamped (row-in-chunk = ly), all three accumulator roles are live, no
+        // staging traffic.  They run as one straight-line block per step so the scheduler can overlap the
+        // shuffle reduction of the completing row with the FFMA2 chains of the other two.
+        const float* lane_base = sring + ly * kRowF + 32 * g;
+        const bool has_q2 = ly < kKW - 2 * kS;
+        const bool hi = (ly & 4) != 0, mid = (ly & 2) != 0;
+        auto fast = [&](const int i, u64 (&F)[4], u64 (&M)[4], u64 (&L)[4]) {
+            if (MODE != 2) mbar_wait(sfull + 8 * slot, par);
+            const float* src = lane_base + (size_t)slot * kChunkF;
+            u64 E[kLoadP];
+#pragma unroll
+            for (int j = 0; j < kLoadF / 4; ++j) {
+                const ulonglong2 t = reinterpret_cast<const ulonglong2*>(src)[j];
+                E[2 * j] = t.x; E[2 * j + 1] = t.y;
+            }
+            __syncwarp();
+            if (lane == 0 && MODE != 2) mbar_arrive(sempty + 8 * slot);
+            if (++slot == kDepth) { slot = 0; par ^= 1; }
+            if (left_edge) {
+                const float v = lo2(E[4]);
+                E[1] = E[2] = E[3] = pack2(v, v);
+            }
+            if (right_edge) {
+                const float v = hi2(E[19]);
+                E[20] = E[21] = E[22] = pack2(v, v);
+            }
+#pragma unroll
+            for (int m = 1; m < kLoadP - 1; ++m) E[m] = add2(E[m], npv2);
+            if (MODE == 1) {
+                F[0] = add2(F[0], add2(E[1], E[22]));
+                if (writer && lo2(F[0]) == 123.456f) out[(long long)(i - 2) * a.Wo] = lo2(F[0]);
+                return;
+            }
+            // completing row first: lanes with ly >= 4 keep L as it is (see the NaN note in `step`)
+            u64 Lt[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                Lt[x] = L[x];
+#pragma unroll
+                for (int t = 0; t < kTapPairs; ++t) Lt[x] = fma2(W[2][t], E[4 * x + 1 + t], Lt[x]);
+                if (has_q2) L[x] = Lt[x];
+            }
+            const float a0 = lo2(L[0]) + hi2(L[0]), a1 = lo2(L[1]) + hi2(L[1]);
+            const float a2 = lo2(L[2]) + hi2(L[2]), a3 = lo2(L[3]) + hi2(L[3]);
+            float k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
+            const float s0 = hi ? a0 : a2, s1 = hi ? a1 : a3;
+            k0 += __shfl_xor_sync(0xffffffffu, s0, 4);
+            k1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int t = 0; t < kTapPairs; ++t) M[x] = fma2(W[1][t], E[4 * x + 1 + t], M[x]);
+            float k = mid ? k1 : k0;
+            const float sx = mid ? k0 : k1;
+            k += __shfl_xor_sync(0xffffffffu, sx, 2);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                F[x] = mul2(W[0][0], E[4 * x + 1]);
+#pragma unroll
+                for (int t = 1; t < kTapPairs; ++t) F[x] = fma2(W[0][t], E[4 * x + 1 + t], F[x]);
+            }
+            k += __shfl_xor_sync(0xffffffffu, k, 1);
+            if (writer) {
+                float res = pv + fmaf(pv, ds, k);
+                if (noisy) res = fmaf(scale, nzs[(i - 2) * 16], res);
+                out[(long long)(i - 2) * a.Wo] = res;
+            }
+        };
+
+        int i = 0;
 #pragma unroll 1
-        for (int i = 0; i < nsteps; i += 3) {
-            step(i, A0, A1, A2);
-            if (i + 1 < nsteps) step(i + 1, A2, A0, A1);
-            if (i + 2 < nsteps) step(i + 2, A1, A2, A0);
+        while (i < nsteps) {
+            if (i >= 3 && i + 2 < a.Ho) {
+                fast(i, A0, A1, A2);
+                fast(i + 1, A2, A0, A1);
+                fast(i + 2, A1, A2, A0);
+                i += 3;
+            } else {
+                step(i, A0, A1, A2);
+                // rotate roles by value: the next step's (F, M, L) = this step's (L, F, M)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) { const u64 t = A2[x]; A2[x] = A1[x]; A1[x] = A0[x]; A0[x] = t; }
+                ++i;
+            }
         }
         // the last chunk of the band: both the step that loaded it and the bottom-halo step are done
         __syncwarp();
