@@ -152,7 +152,7 @@ def run_reference(args):
     orc.multi_kernel_pairs(probe, kbank, sbank, pool, kidx_all[:8], nidx_all[:8], FACTOR)
     per_patch = (time.perf_counter() - t0) / 8
     budget = 150.0
-    sample = int(max(8, min(256, budget / max(per_patch, 1e-6) / (args.steps + args.warmup))))
+    sample = int(max(8, min(256, args.patches, budget / max(per_patch, 1e-6) / (args.steps + args.warmup))))
     hr = np.concatenate([synth.make_hr(sample // 2, 1234, "textured"), synth.make_hr(sample - sample // 2, 1235, "water")])
     ki, ni = kidx_all[:sample], nidx_all[:sample]
     for _ in range(args.warmup):
@@ -167,8 +167,11 @@ def run_reference(args):
         "impl": "reference", "metric": "LR/HR patch pairs/sec", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C_31 multi-kernel apply + sigma noise (BASELINE config 2)", "patches": args.patches,
-                   "patch": [C, P, P], "kernel": K_SIZE, "factor": FACTOR, "noise_pool": POOL_N},
+        "config": {"workload": "C_31 multi-kernel apply + sigma noise (BASELINE config 2)",
+                   "patches_per_gpu": args.patches, "patch": [C, P, P], "kernel": K_SIZE, "factor": FACTOR,
+                   "noise_pool": POOL_N, "kernel_bank": "10 shipped moe_kernels + sigmas",
+                   "algo": "reference CPU path (torch F.pad / F.conv2d / F.avg_pool2d + numpy), rank 0 only",
+                   "sample_patches_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

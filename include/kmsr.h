@@ -123,6 +123,41 @@ KMSR_API int kmsr_degrade_prepared(const float* hr, int64_t N, int C, int H, int
                                    int factor, int pad_mode, int down_mode, int noise_mode,
                                    float* lr, int algo, void* stream);
 
+/* Scene-scale form (BASELINE config 4): the N patches are H x W WINDOWS of one resident scene
+ * [C, scene_h, scene_w] (band stride hr_stride_c, row stride hr_stride_h), window n starting at element
+ * offset patch_offsets[n] of band 0 -- the windows A_00_patch_cutter_universal.py:166-176 cuts, never
+ * materialised.  Replicate padding clamps to the WINDOW (patches are cut first, then blurred).  Knowing
+ * the scene extents lets the TMA kernel stream windows straight from the scene (overlapping windows are
+ * served by L2); `x_multiple` is the caller's promise that every window's left column is a multiple of
+ * it (the TMA kernel needs a multiple of 4; pass 1 if unknown and the tiled kernel runs).            */
+KMSR_API int kmsr_degrade_windows(const float* scene, int C, int scene_h, int scene_w,
+                                  int64_t hr_stride_c, int64_t hr_stride_h,
+                                  const int64_t* patch_offsets, int64_t N, int H, int W, int x_multiple,
+                                  const float* comp, const float* dsum, int64_t nK, int kh, int kw,
+                                  const int32_t* kidx,
+                                  const float* sigma, const float* pool, int64_t nPool,
+                                  const int32_t* nidx,
+                                  int factor, int pad_mode, int down_mode, int noise_mode,
+                                  float* lr, int algo, void* stream);
+
+/* Pair generation AND per-band statistics of the HR patches in one pass (BASELINE config 3:
+ * E_make_train_data.py:223-250 + data_mean_std.py:32-33): same as kmsr_degrade_prepared on contiguous
+ * [N, C, H, W] patches (patch stride hr_stride_n), plus mean / std [N, C] float64 and the accumulated
+ * `sums` [2C+1] of kmsr_band_stats.  When the TMA kernel takes the call the sums of x and x^2 are
+ * gathered from the pixels while they sit in registers (HR crosses HBM once); bands that contain NaN are
+ * redone by the exact NaN-skipping two-pass kernel.  Otherwise degrade and band_stats run back to back.
+ * workspace: kmsr_degrade_stats_workspace_bytes(N, C).                                              */
+KMSR_API int64_t kmsr_degrade_stats_workspace_bytes(int64_t N, int C);
+KMSR_API int kmsr_degrade_stats_prepared(const float* hr, int64_t N, int C, int H, int W,
+                                         int64_t hr_stride_n,
+                                         const float* comp, const float* dsum, int64_t nK, int kh, int kw,
+                                         const int32_t* kidx,
+                                         const float* sigma, const float* pool, int64_t nPool,
+                                         const int32_t* nidx,
+                                         int factor, int pad_mode, int down_mode, int noise_mode,
+                                         float* lr, double* mean, double* std, double* sums,
+                                         void* workspace, int64_t workspace_bytes, int algo, void* stream);
+
 /* kmsr_prepare_kernels into `workspace`, then kmsr_degrade_prepared, on the same stream. */
 KMSR_API int kmsr_degrade_batch(const float* hr, int64_t N, int C, int H, int W,
                                 int64_t hr_stride_n, int64_t hr_stride_c, int64_t hr_stride_h,

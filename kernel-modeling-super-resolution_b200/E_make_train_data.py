@@ -41,7 +41,7 @@ def add_noise(blurred: np.ndarray, noise_pool: np.ndarray) -> np.ndarray:
 
 
 def make_pairs(hr, kernel, noise_pool, seed: int | None = 42, downscale_factor: int = 8,
-               hr_size: int = 256, lr_size: int = 32):
+               hr_size: int = 256, lr_size: int = 32, with_stats: bool = False, sums=None):
     """Batched E.process_files arithmetic: hr [N,5,256,256] -> (hr, lr [N,5,32,32], nidx).
 
     Equivalent to C_30.apply_kernel_degradation on every patch followed by E.add_noise in file
@@ -58,8 +58,15 @@ def make_pairs(hr, kernel, noise_pool, seed: int | None = 42, downscale_factor: 
     k = kernel if isinstance(kernel, torch.Tensor) else torch.as_tensor(np.asarray(kernel, dtype=np.float32))
     if k.ndim == 2:
         k = k.unsqueeze(0).repeat(t.shape[1], 1, 1)
-    lr = ops.degrade_batch(t.to(device=dev, dtype=torch.float32), k.to(dev), pool=pool, nidx=nidx,
-                           factor=int(downscale_factor), noise_mode="add")
+    if with_stats:
+        # data_mean_std.py:32-33 over the HR patches in the same pass: returns (hr, lr, nidx, mean, std)
+        lr, mean, std = ops.degrade_batch_stats(t.to(device=dev, dtype=torch.float32), k.to(dev), pool=pool, nidx=nidx,
+                                                factor=int(downscale_factor), noise_mode="add", sums=sums)
+    else:
+        lr = ops.degrade_batch(t.to(device=dev, dtype=torch.float32), k.to(dev), pool=pool, nidx=nidx,
+                               factor=int(downscale_factor), noise_mode="add")
     if lr.shape[-1] != lr_size or lr.shape[-2] != lr_size:                     # E:244-247
         raise ValueError(f"LR patches must be {lr_size}x{lr_size}, got {tuple(lr.shape[-2:])}")
+    if with_stats:
+        return t, (lr if t.is_cuda else lr.cpu()), nidx, mean, std
     return t, (lr if t.is_cuda else lr.cpu()), nidx

@@ -44,6 +44,13 @@ SIGNATURES = {
     "kmsr_degrade_prepared": (_i32, [_vp, _i64, _i32, _i32, _i32, _i64, _i64, _i64, _vp,
                                      _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp,
                                      _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "kmsr_degrade_windows": (_i32, [_vp, _i32, _i32, _i32, _i64, _i64, _vp, _i64, _i32, _i32, _i32,
+                                    _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp,
+                                    _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "kmsr_degrade_stats_workspace_bytes": (_i64, [_i64, _i32]),
+    "kmsr_degrade_stats_prepared": (_i32, [_vp, _i64, _i32, _i32, _i32, _i64,
+                                           _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp,
+                                           _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "kmsr_degrade_batch": (_i32, [_vp, _i64, _i32, _i32, _i32, _i64, _i64, _i64, _vp,
                                   _vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp,
                                   _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp]),

@@ -27,6 +27,8 @@ int launch_crop_sub(const float*, const float*, int, int, int, const int*, const
 int launch_band_stats(const float*, long long, int, long long, long long, double*, double*, double*,
                       cudaStream_t);
 int launch_water_mask(float*, int, long long, int, float, float, float, float*, cudaStream_t);
+int launch_stats_finish(const double*, const float*, long long, int, long long, long long, double*, double*,
+                        double*, cudaStream_t);
 long long keep_mask_workspace(int, int, int, int);
 int launch_keep_mask(const float*, int, int, int, int, int, double, unsigned char*, int*, void*,
                      long long, cudaStream_t);
@@ -92,13 +94,16 @@ KMSR_API int kmsr_prepare_kernels(const float* kbank, int64_t nK, int C, int kh,
     return launch_prepare(kbank, nK, C, kh, kw, factor, down_mode, comp, dsum, (cudaStream_t)stream);
 }
 
-KMSR_API int kmsr_degrade_prepared(const float* hr, int64_t N, int C, int H, int W, int64_t hr_stride_n,
-                                   int64_t hr_stride_c, int64_t hr_stride_h, const int64_t* patch_offsets,
-                                   const float* comp, const float* dsum, int64_t nK, int kh, int kw,
-                                   const int32_t* kidx, const float* sigma, const float* pool,
-                                   int64_t nPool, const int32_t* nidx, int factor, int pad_mode,
-                                   int down_mode, int noise_mode, float* lr, int algo, void* stream) {
+static int degrade_common(const float* hr, int64_t N, int C, int H, int W, int64_t hr_stride_n,
+                          int64_t hr_stride_c, int64_t hr_stride_h, const int64_t* patch_offsets, int scene_h,
+                          int scene_w, int x_multiple,
+                          const float* comp, const float* dsum, int64_t nK, int kh, int kw,
+                          const int32_t* kidx, const float* sigma, const float* pool,
+                          int64_t nPool, const int32_t* nidx, int factor, int pad_mode,
+                          int down_mode, int noise_mode, float* lr, int algo, void* stream,
+                          double* stat_part = nullptr) {
     DegradeArgs a;
+    a.stat_part = stat_part;
     int rc = make_geometry(H, W, kh, kw, factor, down_mode, &a.g);
     KMSR_REQUIRE(rc == KMSR_OK, rc, "degrade: bad geometry H=%d W=%d k=%dx%d factor=%d down_mode=%d", H, W, kh,
                  kw, factor, down_mode);
@@ -121,6 +126,7 @@ KMSR_API int kmsr_degrade_prepared(const float* hr, int64_t N, int C, int H, int
     a.hr = hr; a.N = N; a.C = C; a.H = H; a.W = W;
     a.sN = hr_stride_n; a.sC = hr_stride_c; a.sH = hr_stride_h;
     a.patch_offsets = (const long long*)patch_offsets;
+    a.scene_h = scene_h; a.scene_w = scene_w; a.x_multiple = x_multiple;
     a.comp = comp; a.dsum = dsum; a.nK = nK; a.kidx = kidx;
     a.sigma = sigma; a.pool = pool; a.nPool = nPool; a.nidx = nidx;
     a.pad_mode = pad_mode; a.noise_mode = noise_mode; a.lr = lr;
@@ -133,6 +139,70 @@ KMSR_API int kmsr_degrade_prepared(const float* hr, int64_t N, int C, int H, int
     }
     if (algo == KMSR_ALGO_AUTO && tma_ok) return launch_degrade_tma(a, st);
     return launch_degrade_tiled(a, st);
+}
+
+KMSR_API int kmsr_degrade_prepared(const float* hr, int64_t N, int C, int H, int W, int64_t hr_stride_n,
+                                   int64_t hr_stride_c, int64_t hr_stride_h, const int64_t* patch_offsets,
+                                   const float* comp, const float* dsum, int64_t nK, int kh, int kw,
+                                   const int32_t* kidx, const float* sigma, const float* pool,
+                                   int64_t nPool, const int32_t* nidx, int factor, int pad_mode,
+                                   int down_mode, int noise_mode, float* lr, int algo, void* stream) {
+    return degrade_common(hr, N, C, H, W, hr_stride_n, hr_stride_c, hr_stride_h, patch_offsets, 0, 0, 1, comp, dsum,
+                          nK, kh, kw, kidx, sigma, pool, nPool, nidx, factor, pad_mode, down_mode, noise_mode, lr,
+                          algo, stream);
+}
+
+KMSR_API int kmsr_degrade_windows(const float* scene, int C, int scene_h, int scene_w, int64_t hr_stride_c,
+                                  int64_t hr_stride_h, const int64_t* patch_offsets, int64_t N, int H, int W,
+                                  int x_multiple, const float* comp, const float* dsum, int64_t nK, int kh,
+                                  int kw, const int32_t* kidx, const float* sigma, const float* pool,
+                                  int64_t nPool, const int32_t* nidx, int factor, int pad_mode, int down_mode,
+                                  int noise_mode, float* lr, int algo, void* stream) {
+    KMSR_REQUIRE(scene_h >= H && scene_w >= W && H >= 1 && W >= 1, KMSR_E_INVALID,
+                 "degrade_windows: window %dx%d does not fit the scene %dx%d", H, W, scene_h, scene_w);
+    KMSR_REQUIRE(hr_stride_h >= scene_w && hr_stride_c >= (int64_t)scene_h * hr_stride_h - (hr_stride_h - scene_w),
+                 KMSR_E_INVALID, "degrade_windows: strides (%lld, %lld) do not hold a %dx%d scene",
+                 (long long)hr_stride_c, (long long)hr_stride_h, scene_h, scene_w);
+    KMSR_REQUIRE(N == 0 || patch_offsets != nullptr, KMSR_E_INVALID, "degrade_windows: null patch_offsets");
+    KMSR_REQUIRE(x_multiple >= 1, KMSR_E_INVALID, "degrade_windows: x_multiple %d", x_multiple);
+    return degrade_common(scene, N, C, H, W, 0, hr_stride_c, hr_stride_h, patch_offsets, scene_h, scene_w, x_multiple,
+                          comp, dsum, nK, kh, kw, kidx, sigma, pool, nPool, nidx, factor, pad_mode, down_mode,
+                          noise_mode, lr, algo, stream);
+}
+
+KMSR_API int64_t kmsr_degrade_stats_workspace_bytes(int64_t N, int C) {
+    if (N < 0 || C < 1) { set_error("degrade_stats_workspace_bytes: N=%lld C=%d", (long long)N, C); return KMSR_E_INVALID; }
+    return N * C * 4 * (int64_t)sizeof(double) + 256;
+}
+
+KMSR_API int kmsr_degrade_stats_prepared(const float* hr, int64_t N, int C, int H, int W, int64_t hr_stride_n,
+                                         const float* comp, const float* dsum, int64_t nK, int kh, int kw,
+                                         const int32_t* kidx, const float* sigma, const float* pool,
+                                         int64_t nPool, const int32_t* nidx, int factor, int pad_mode,
+                                         int down_mode, int noise_mode, float* lr, double* mean, double* std,
+                                         double* sums, void* workspace, int64_t workspace_bytes, int algo,
+                                         void* stream) {
+    KMSR_REQUIRE(mean && std, KMSR_E_INVALID, "degrade_stats: null mean / std");
+    const int64_t hw = (int64_t)H * W;
+    KMSR_REQUIRE(N <= 1 || hr_stride_n >= (int64_t)C * hw, KMSR_E_INVALID, "degrade_stats: patch stride %lld < C*H*W",
+                 (long long)hr_stride_n);
+    const int64_t need = kmsr_degrade_stats_workspace_bytes(N, C);
+    KMSR_REQUIRE(workspace && workspace_bytes >= need, KMSR_E_INVALID,
+                 "degrade_stats: workspace of %lld B needed, %lld given", (long long)need, (long long)workspace_bytes);
+    double* part = (double*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    // fused when the TMA kernel takes the call, otherwise the two kernels run back to back (same results contract)
+    DegradeArgs probe;
+    int rc = make_geometry(H, W, kh, kw, factor, down_mode, &probe.g);
+    KMSR_REQUIRE(rc == KMSR_OK, rc, "degrade_stats: bad geometry");
+    probe.hr = hr; probe.N = N; probe.C = C; probe.H = H; probe.W = W; probe.sN = hr_stride_n; probe.sC = hw; probe.sH = W;
+    probe.patch_offsets = nullptr; probe.scene_h = probe.scene_w = 0; probe.x_multiple = 1; probe.pad_mode = pad_mode;
+    const char* why = "";
+    const bool fused = algo != KMSR_ALGO_TILED && N > 0 && tma_shape_ok(probe, &why);
+    rc = degrade_common(hr, N, C, H, W, hr_stride_n, hw, W, nullptr, 0, 0, 1, comp, dsum, nK, kh, kw, kidx, sigma, pool,
+                        nPool, nidx, factor, pad_mode, down_mode, noise_mode, lr, algo, stream, fused ? part : nullptr);
+    if (rc != KMSR_OK || N == 0) return rc;
+    if (fused) return launch_stats_finish(part, hr, N, C, hw, hr_stride_n, mean, std, sums, (cudaStream_t)stream);
+    return launch_band_stats(hr, N, C, hw, hr_stride_n, mean, std, sums, (cudaStream_t)stream);
 }
 
 KMSR_API int kmsr_degrade_batch(const float* hr, int64_t N, int C, int H, int W, int64_t hr_stride_n,

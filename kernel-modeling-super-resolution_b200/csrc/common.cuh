@@ -90,6 +90,7 @@ struct DegradeArgs {
     int C, H, W;
     long long sN, sC, sH;
     const long long* patch_offsets;
+    int scene_h, scene_w, x_multiple;   // extents of the tensor the windows live in (0 = unknown)
     const float* comp;   // [nK, C, KH, KWp]
     const float* dsum;   // [nK, C]
     long long nK;
@@ -100,6 +101,7 @@ struct DegradeArgs {
     const int* nidx;
     int pad_mode, noise_mode;
     float* lr;
+    double* stat_part;   // fused statistics partials [N*C][2][2] (TMA kernel only), or nullptr
     Geometry g;
 };
 

@@ -77,6 +77,9 @@ struct TmaArgs {
     int C, H, Ho, Wo;
     int nchunks;      // H/8 + 1
     int noise_mode;
+    const long long* offs;   // scene windows: element offset of window n in band 0 (else nullptr)
+    long long sH;            // scene row stride in elements (windows only)
+    double* stat_part;       // STATS: [nbands][2 warps][sum x, sum x^2] (data_mean_std.py:32-33 fused), else nullptr
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -178,7 +181,9 @@ constexpr int kLoadP = kLoadF / 2;             // 24 pixel pairs per lane and st
 // MODE 0 = product kernel.  MODE 1 / 2 are measurement aids selected by KMSR_TMA_DEBUG (bench only):
 // 1 = feed only (consumers wait, release and skip the arithmetic: TMA / HBM side alone),
 // 2 = compute only (no TMA, no waits: SM side alone, results meaningless).
-template <int MODE>
+// STATS fuses the per-band sum / sum of squares of data_mean_std.py:32-33 into the pass: every HR pixel is in
+// registers exactly once as "own column" of one lane (floats 8..39 of its segment), already pivot-shifted.
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -217,6 +222,25 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
         const uint32_t sfull = full0 + 8 * s * kDepth, sempty = empty0 + 8 * s * kDepth;
         float* sring = ring + (size_t)s * kDepth * kChunkF;
         const uint64_t policy = l2_evict_first_policy();
+        if (a.offs) {
+            // scene windows: the map is the scene [W_s/2, H_s, C, 1]; overlapping windows are re-read
+            // through L2 (default policy), rows / columns outside the window are never consumed
+            while (band < a.nbands) {
+                const long long off = __ldg(a.offs + pn);
+                const int y0 = (int)(off / a.sH);
+                const int x0 = (int)(off - (long long)y0 * a.sH);
+                for (int chunk = 0; chunk < a.nchunks; ++chunk) {
+                    mbar_wait_relaxed(sempty + 8 * slot, par);
+                    mbar_arrive_expect_tx(sfull + 8 * slot, kChunkBytes);
+                    tma_load_4d(smem_u32(sring + (size_t)slot * kChunkF), &tmap, x0 / 2 - kLeftF / 2,
+                                y0 + kS * chunk - kPad, pc, 0, sfull + 8 * slot);
+                    if (++slot == kDepth) { slot = 0; par ^= 1; }
+                }
+                band += G; pn += Gn; pc += Gc;
+                if (pc >= a.C) { pc -= a.C; ++pn; }
+            }
+            return;
+        }
         while (band < a.nbands) {
             mbar_wait_relaxed(sempty + 8 * slot, par);
             mbar_arrive_expect_tx(sfull + 8 * slot, kChunkBytes);
@@ -328,6 +352,20 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
 
         float pv = 0.0f;
         u64 npv2 = 0ull;
+        double sd1 = 0.0, sd2 = 0.0;       // STATS: sum (x - pv), sum (x - pv)^2 over this lane's own pixels
+        // own pixels of a row: columns 32g .. 32g+31 = pixel pairs E[4 .. 19], never edge-substituted
+        auto stat_acc = [&](const u64 (&E)[kLoadP]) {
+            u64 p1a = E[4], p1b = E[5];
+            u64 p2a = mul2(E[4], E[4]), p2b = mul2(E[5], E[5]);
+#pragma unroll
+            for (int m = 6; m < 20; m += 2) {
+                p1a = add2(p1a, E[m]); p1b = add2(p1b, E[m + 1]);
+                p2a = fma2(E[m], E[m], p2a); p2b = fma2(E[m + 1], E[m + 1], p2b);
+            }
+            const u64 p1 = add2(p1a, p1b), p2 = add2(p2a, p2b);
+            sd1 += (double)(lo2(p1) + hi2(p1));
+            sd2 += (double)(lo2(p2) + hi2(p2));
+        };
         u64 A0[4], A1[4], A2[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) A0[x] = A1[x] = A2[x] = 0ull;
@@ -383,6 +421,10 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
             }
 #pragma unroll
             for (int m = 1; m < kLoadP - 1; ++m) E[m] = add2(E[m], npv2);
+            if (STATS) {
+                const int rr = kS * i + ly - kPad;                 // unclamped: halo rows are not pixels of the band
+                if (rr >= 0 && rr < a.H) stat_acc(E);
+            }
 
             if (MODE == 1) {                       // feed-only measurement: keep one dependency on the data
                 F[0] = add2(F[0], add2(E[1], E[22]));
@@ -463,6 +505,7 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
             }
 #pragma unroll
             for (int m = 1; m < kLoadP - 1; ++m) E[m] = add2(E[m], npv2);
+            if (STATS) stat_acc(E);
             if (MODE == 1) {
                 F[0] = add2(F[0], add2(E[1], E[22]));
                 if (writer && lo2(F[0]) == 123.456f) out[(long long)(i - 2) * a.Wo] = lo2(F[0]);
@@ -524,6 +567,21 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
         __syncwarp();
         if (lane == 0 && MODE != 2) mbar_arrive(sempty + 8 * slot);
         if (++slot == kDepth) { slot = 0; par ^= 1; }
+        if (STATS) {
+            // absolute sums of this lane's H/8 rows x 32 columns, then over the warp (fixed xor tree: deterministic)
+            const double nl = (double)(a.H / kS) * 32.0, p = (double)pv;
+            double t1 = sd1 + nl * p;
+            double t2 = sd2 + 2.0 * p * sd1 + nl * p * p;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+                t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+            }
+            if (lane == 0) {
+                a.stat_part[(band * 2 + half) * 2] = t1;
+                a.stat_part[(band * 2 + half) * 2 + 1] = t2;
+            }
+        }
         n = nn; c = nc;
     }
 }
@@ -553,11 +611,15 @@ bool tma_shape_ok(const DegradeArgs& a, const char** why) {
     if (a.pad_mode != KMSR_PAD_REPLICATE) { *why = "needs replicate padding"; return false; }
     if (a.W != 256) { *why = "needs W == 256"; return false; }
     if (a.H < 8 || a.H % 8 != 0 || a.H > 8 * kMaxHo) { *why = "needs H % 8 == 0 and H <= 256"; return false; }
-    if (a.patch_offsets) { *why = "patch_offsets (scene windows) not covered"; return false; }
-    if (((uintptr_t)a.hr & 15) || (a.sH & 3) || (a.sC & 3) || (a.N > 1 && (a.sN & 3))) {
+    if (a.patch_offsets) {
+        if (a.scene_h <= 0 || a.scene_w <= 0) { *why = "patch_offsets without scene extents (use kmsr_degrade_windows)"; return false; }
+        if (a.x_multiple % 4 != 0) { *why = "window columns not promised to be multiples of 4"; return false; }
+        if (a.scene_w % 2 != 0) { *why = "odd scene width"; return false; }
+    }
+    if (((uintptr_t)a.hr & 15) || (a.sH & 3) || (a.sC & 3) || (!a.patch_offsets && a.N > 1 && (a.sN & 3))) {
         *why = "HR base / strides not 16-byte aligned"; return false;
     }
-    if (a.sH < a.W || a.sC < 1 || (a.N > 1 && a.sN < 1)) { *why = "non-positive strides"; return false; }
+    if (a.sH < a.W || a.sC < 1 || (!a.patch_offsets && a.N > 1 && a.sN < 1)) { *why = "non-positive strides"; return false; }
     if (a.N >= (1ll << 31) || a.N * a.C >= (1ll << 40)) { *why = "too many patches"; return false; }
     return true;
 }
@@ -566,9 +628,12 @@ int launch_degrade_tma(const DegradeArgs& a, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
     KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "degrade (tma): cuTensorMapEncodeTiled is not available from the driver");
     CUtensorMap tmap;
-    // [N, C, H, W/2] of 64-bit elements; box = 138 x 8 x 1 x 1 (x starts at -4: zero-filled halo)
-    cuuint64_t gdim[4] = {(cuuint64_t)(a.W / 2), (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.N};
-    const long long sN = a.N > 1 ? a.sN : (long long)a.C * a.sC;
+    // [N, C, H, W/2] of 64-bit elements; box = 138 x 8 x 1 x 1 (x starts at -4: zero-filled halo).
+    // Scene windows: [1, C, H_s, W_s/2], the box origin follows the window.
+    const bool win = a.patch_offsets != nullptr;
+    cuuint64_t gdim[4] = {(cuuint64_t)((win ? a.scene_w : a.W) / 2), (cuuint64_t)(win ? a.scene_h : a.H), (cuuint64_t)a.C,
+                          (cuuint64_t)(win ? 1 : a.N)};
+    const long long sN = (!win && a.N > 1) ? a.sN : (long long)a.C * a.sC;
     cuuint64_t gstr[3] = {(cuuint64_t)a.sH * 4, (cuuint64_t)a.sC * 4, (cuuint64_t)sN * 4};
     cuuint32_t box[4] = {(cuuint32_t)(kRowF / 2), 8, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -581,6 +646,7 @@ int launch_degrade_tma(const DegradeArgs& a, cudaStream_t st) {
     t.comp = a.comp; t.dsum = a.dsum; t.kidx = a.kidx; t.sigma = a.sigma; t.pool = a.pool; t.nidx = a.nidx;
     t.lr = a.lr; t.nbands = a.N * a.C; t.C = a.C; t.H = a.H; t.Ho = a.g.Ho; t.Wo = a.g.Wo;
     t.nchunks = a.H / 8 + 1; t.noise_mode = a.noise_mode;
+    t.offs = a.patch_offsets; t.sH = a.sH;
 
     int dev = 0, sms = 0;
     KMSR_CUDA_OK(cudaGetDevice(&dev));
@@ -589,15 +655,19 @@ int launch_degrade_tma(const DegradeArgs& a, cudaStream_t st) {
     if (grid > (long long)kCtasPerSm * sms) grid = (long long)kCtasPerSm * sms;
     static const int debug_mode = [] { const char* e = getenv("KMSR_TMA_DEBUG"); return e ? atoi(e) : 0; }();
     set_algo("tma");
-    if (debug_mode == 1) {
-        KMSR_CUDA_OK(cudaFuncSetAttribute(degrade_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        degrade_tma_kernel<1><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tmap, t);
+    t.stat_part = a.stat_part;
+    if (a.stat_part) {
+        KMSR_CUDA_OK(cudaFuncSetAttribute(degrade_tma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        degrade_tma_kernel<0, true><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tmap, t);
+    } else if (debug_mode == 1) {
+        KMSR_CUDA_OK(cudaFuncSetAttribute(degrade_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        degrade_tma_kernel<1, false><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tmap, t);
     } else if (debug_mode == 2) {
-        KMSR_CUDA_OK(cudaFuncSetAttribute(degrade_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        degrade_tma_kernel<2><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tmap, t);
+        KMSR_CUDA_OK(cudaFuncSetAttribute(degrade_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        degrade_tma_kernel<2, false><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tmap, t);
     } else {
-        KMSR_CUDA_OK(cudaFuncSetAttribute(degrade_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        degrade_tma_kernel<0><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tmap, t);
+        KMSR_CUDA_OK(cudaFuncSetAttribute(degrade_tma_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        degrade_tma_kernel<0, false><<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tmap, t);
     }
     KMSR_LAUNCH_CHECK("degrade_tma_kernel");
     return KMSR_OK;

@@ -22,11 +22,18 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
+// ONLY_NAN: recompute only the bands whose fused result came out NaN (a NaN pixel poisons the fused
+// sums; np.nanmean / np.nanstd skip it) -- every other CTA leaves at once.
+template <bool ONLY_NAN>
 __global__ void __launch_bounds__(256)
 band_stats_kernel(const float* __restrict__ x, int C, long long hw, long long stride_n,
                   double* __restrict__ mean, double* __restrict__ stdv) {
     __shared__ double red[8];
     const long long band = blockIdx.x;
+    if (ONLY_NAN) {
+        const double m0 = mean[band], s0 = stdv[band];
+        if (m0 == m0 && s0 == s0) return;
+    }
     const long long n = band / C;
     const int c = (int)(band % C);
     const float* p = x + n * stride_n + (long long)c * hw;
@@ -110,7 +117,38 @@ int launch_band_stats(const float* x, long long N, int C, long long hw, long lon
     if (N == 0) return KMSR_OK;
     KMSR_REQUIRE(N * C < (1ll << 31), KMSR_E_INVALID, "band_stats: N*C too large");
     KMSR_REQUIRE(hw > 0, KMSR_E_INVALID, "band_stats: empty bands");
-    band_stats_kernel<<<(unsigned)(N * C), 256, 0, st>>>(x, C, hw, stride_n, mean, stdv);
+    band_stats_kernel<false><<<(unsigned)(N * C), 256, 0, st>>>(x, C, hw, stride_n, mean, stdv);
+    KMSR_LAUNCH_CHECK("band_stats_kernel");
+    if (sums) {
+        stats_reduce_kernel<<<2 * C + 1, 256, 0, st>>>(mean, stdv, N, C, sums);
+        KMSR_LAUNCH_CHECK("stats_reduce_kernel");
+    }
+    return KMSR_OK;
+}
+
+// Fused path (degrade_tma_kernel<0, true>): part[band][warp][sum x, sum x^2] -> population mean / std.
+__global__ void __launch_bounds__(256)
+stats_finish_kernel(const double* __restrict__ part, long long nbands, double npix, double* __restrict__ mean,
+                    double* __restrict__ stdv) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= nbands) return;
+    const double s1 = part[4 * b] + part[4 * b + 2];
+    const double s2 = part[4 * b + 1] + part[4 * b + 3];
+    const double m = s1 / npix;
+    double v = s2 / npix - m * m;
+    if (v < 0.0) v = 0.0;
+    mean[b] = m;
+    stdv[b] = sqrt(v);           // NaN in, NaN out: those bands are redone by band_stats_kernel<true>
+}
+
+int launch_stats_finish(const double* part, const float* x, long long N, int C, long long hw, long long stride_n,
+                        double* mean, double* stdv, double* sums, cudaStream_t st) {
+    if (N == 0) return KMSR_OK;
+    const long long nb = N * C;
+    KMSR_REQUIRE(nb < (1ll << 31), KMSR_E_INVALID, "stats: N*C too large");
+    stats_finish_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(part, nb, (double)hw, mean, stdv);
+    KMSR_LAUNCH_CHECK("stats_finish_kernel");
+    band_stats_kernel<true><<<(unsigned)nb, 256, 0, st>>>(x, C, hw, stride_n, mean, stdv);
     KMSR_LAUNCH_CHECK("band_stats_kernel");
     if (sums) {
         stats_reduce_kernel<<<2 * C + 1, 256, 0, st>>>(mean, stdv, N, C, sums);

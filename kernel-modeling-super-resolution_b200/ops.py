@@ -78,12 +78,15 @@ def degrade_batch(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, 
                   factor: int = 8, pad_mode: str = "replicate", down_mode: str = "boxmean",
                   noise_mode: str | None = None, out: torch.Tensor | None = None, algo: str = "auto",
                   patch_offsets: torch.Tensor | None = None, patch_hw: tuple[int, int] | None = None,
-                  strides: tuple[int, int, int] | None = None, n_patches: int | None = None) -> torch.Tensor:
+                  strides: tuple[int, int, int] | None = None, n_patches: int | None = None,
+                  scene_hw: tuple[int, int] | None = None, x_multiple: int = 1) -> torch.Tensor:
     """lr[n,c] = degrade(hr[n], K[kidx[n]])[c] (+ scale * pool[nidx[n], c]) on the device.
 
     hr: CUDA float32 [N, C, H, W] with contiguous rows (any N / C / row strides), or -- with
     `patch_offsets` (int64 element offsets), `patch_hw`, `strides=(sC, sH)` -- a base tensor that the
-    patches are windows of (scene-scale path, A_00_patch_cutter_universal.py:176).
+    patches are windows of (scene-scale path, A_00_patch_cutter_universal.py:176).  With `scene_hw` (extents
+    of that base tensor) and `x_multiple` (every window's left column is a multiple of it; >= 4 for the
+    TMA kernel) the windows stream straight from the scene through kmsr_degrade_windows.
     kbank: tensor [nK,C,kh,kw] / [C,kh,kw] or a PreparedBank.
     """
     require_cuda()
@@ -133,6 +136,14 @@ def degrade_batch(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, 
         npool = pl.shape[0]
         if tuple(pl.shape[1:]) != (Cc, Ho, Wo):
             raise ValueError(f"noise pool {tuple(pl.shape)} does not match LR patches {(Cc, Ho, Wo)}")
+    if po is not None and scene_hw is not None:
+        with torch.cuda.device(dev):
+            L.check(L.lib().kmsr_degrade_windows(
+                _ptr(hr), Cc, int(scene_hw[0]), int(scene_hw[1]), sC, sH, _ptr(po), N, H, W, int(x_multiple),
+                _ptr(bank.comp), _ptr(bank.dsum), bank.nK, bank.kh, bank.kw, _ptr(kidx_d),
+                _ptr(sig), _ptr(pl), npool, _ptr(nidx_d),
+                factor, pm, dm, nm, _ptr(out), L.ALGOS[algo], _stream(dev)))
+        return out
     with torch.cuda.device(dev):
         L.check(L.lib().kmsr_degrade_prepared(
             _ptr(hr), N, Cc, H, W, sN, sC, sH, _ptr(po),
@@ -140,6 +151,51 @@ def degrade_batch(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, 
             _ptr(sig), _ptr(pl), npool, _ptr(nidx_d),
             factor, pm, dm, nm, _ptr(out), L.ALGOS[algo], _stream(dev)))
     return out
+
+
+def degrade_batch_stats(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, nidx=None, factor: int = 8,
+                        pad_mode: str = "replicate", down_mode: str = "boxmean", noise_mode: str | None = None,
+                        out: torch.Tensor | None = None, sums: torch.Tensor | None = None, algo: str = "auto"):
+    """degrade_batch + band_stats of the HR patches in one pass (E_make_train_data.py:223-250 with
+    data_mean_std.py:32-33 fused): returns (lr, mean [N,C] f64, std [N,C] f64); `sums` (f64 [2C+1]) is
+    accumulated as in band_stats.  hr: contiguous CUDA float32 [N, C, H, W]."""
+    require_cuda()
+    if not hr.is_cuda or hr.dtype != torch.float32 or hr.ndim != 4:
+        raise TypeError("degrade_batch_stats expects a CUDA float32 tensor [N,C,H,W]")
+    dev = hr.device
+    dm, pm = L.DOWN_MODES[down_mode], L.PAD_MODES[pad_mode]
+    if noise_mode is None:
+        noise_mode = "none" if nidx is None else ("sigma" if sigma is not None else "add")
+    nm = L.NOISE_MODES[noise_mode]
+    bank = kbank if isinstance(kbank, PreparedBank) else prepare_kernels(kbank.to(dev), factor, dm)
+    if bank.factor != factor or bank.down_mode != dm:
+        raise ValueError("PreparedBank was built for a different factor / down_mode")
+    N, Cc, H, W = hr.shape
+    if not hr[0].is_contiguous() or (N > 1 and hr.stride(0) < Cc * H * W):
+        hr = hr.contiguous()
+    assert Cc == bank.C, f"kernel bands ({bank.C}) != image bands ({Cc})"
+    Ho, Wo = L.degrade_out_size(H, W, bank.kh, bank.kw, factor, dm)
+    if out is None:
+        out = torch.empty((N, Cc, Ho, Wo), dtype=torch.float32, device=dev)
+    kidx_d, nidx_d = _i32(kidx, dev), _i32(nidx, dev)
+    sig = None if sigma is None else _f32(torch.as_tensor(sigma), dev).contiguous()
+    pl, npool = None, 0
+    if nm != L.NOISE_NONE:
+        if pool is None or nidx_d is None:
+            raise ValueError("noise requested without pool / nidx")
+        pl = pool if (pool.is_cuda and pool.dtype == torch.float32 and pool.is_contiguous()) else _f32(pool, dev).contiguous()
+        npool = pl.shape[0]
+    mean = torch.empty((N, Cc), dtype=torch.float64, device=dev)
+    std = torch.empty((N, Cc), dtype=torch.float64, device=dev)
+    wsb = int(L.check(L.lib().kmsr_degrade_stats_workspace_bytes(N, Cc)))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().kmsr_degrade_stats_prepared(
+            _ptr(hr), N, Cc, H, W, hr.stride(0) if N > 1 else Cc * H * W,
+            _ptr(bank.comp), _ptr(bank.dsum), bank.nK, bank.kh, bank.kw, _ptr(kidx_d),
+            _ptr(sig), _ptr(pl), npool, _ptr(nidx_d), factor, pm, dm, nm, _ptr(out), _ptr(mean), _ptr(std),
+            _ptr(sums), _ptr(ws), wsb, L.ALGOS[algo], _stream(dev)))
+    return out, mean, std
 
 
 def add_noise_batch(blurred: torch.Tensor, pool: torch.Tensor, nidx, *, sigma=None, kidx=None,

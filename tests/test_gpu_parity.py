@@ -200,6 +200,34 @@ def test_band_stats(K, golden, synth, capsys):
     assert np.allclose(r["mean"][ok], m64[ok], rtol=1e-6) and np.allclose(r["std"][ok], s64[ok], rtol=1e-6)
 
 
+def test_fused_pair_statistics(K, synth, bank):
+    """kmsr_degrade_stats_prepared: LR bits identical to the plain call; mean / std of the HR patches
+    within 1e-6 of fp64 (data_mean_std.py:32-33), NaN bands through the exact NaN-skipping kernel,
+    `sums` accumulated like band_stats; the unfused route (tiled kernel) gives the same contract."""
+    kb, _ = bank
+    hr = np.concatenate([synth.make_hr(6, 1290, "textured"), synth.make_hr(6, 1291, "water")])
+    hr[3, 2, 17, 100] = np.nan
+    hr[8, 0, 255, 255] = np.nan
+    pool = synth.make_noise_pool(64, 42)
+    nidx = K.rng.draw_noise_indices(12, 64, 42)
+    hd = torch.from_numpy(hr).cuda()
+    m64, s64, _, _ = orc.radiance_stats_f64(hr)
+    for algo in ("auto", "tiled"):
+        sums = torch.zeros(11, dtype=torch.float64, device="cuda")
+        lr, m, s = K.ops.degrade_batch_stats(hd, torch.from_numpy(kb[4]).cuda(), pool=torch.from_numpy(pool).cuda(),
+                                             nidx=nidx, factor=8, noise_mode="add", sums=sums, algo=algo)
+        assert K.lib.last_algo() == ("tma" if algo == "auto" else "tiled")
+        plain = K.ops.degrade_batch(hd, torch.from_numpy(kb[4]).cuda(), pool=torch.from_numpy(pool).cuda(), nidx=nidx,
+                                    factor=8, noise_mode="add", algo=algo)
+        assert torch.equal(torch.nan_to_num(lr, nan=-1.0), torch.nan_to_num(plain, nan=-1.0))
+        m, s = m.cpu().numpy(), s.cpu().numpy()
+        assert np.isfinite(m).all() and np.isfinite(s).all()
+        assert np.abs(m - m64).max() <= 1e-6 * np.abs(m64).max() and (np.abs(m - m64) <= 1e-6 * np.abs(m64)).all()
+        assert (np.abs(s - s64) <= 1e-6 * s64).all(), float((np.abs(s - s64) / s64).max())
+        sm = sums.cpu().numpy()
+        assert np.allclose(sm[:5], m.sum(axis=0), rtol=1e-12) and np.allclose(sm[5:10], s.sum(axis=0), rtol=1e-12) and sm[10] == 12
+
+
 def test_analyze_radiance_stats_printout(K, golden, tmp_path, capsys):
     """The drop-in prints the same table numbers as the reference did on the same files (S:48-62)."""
     import re
@@ -253,10 +281,15 @@ def test_scene_windows_degrade_like_cut_patches(K, golden, synth, bank):
     total, kept, ij, offsets, dev_scene = K.CUT.create_patches(masked, 256, 0.5, 0.0)
     assert kept > 0
     h, w = masked.shape[1:]
-    for algo in ("tiled", "auto"):
+    for algo, extents in (("tiled", None), ("auto", None), ("auto", (h, w)), ("tma", (h, w))):
         lr = K.ops.degrade_batch(dev_scene, torch.from_numpy(kb[2]).cuda(), factor=8, patch_offsets=offsets,
-                                 patch_hw=(256, 256), strides=(h * w, w), algo=algo).cpu().numpy()
-        for n, (i, j) in enumerate(ij[:6]):
+                                 patch_hw=(256, 256), strides=(h * w, w), algo=algo, scene_hw=extents,
+                                 x_multiple=128).cpu().numpy()
+        # with the scene extents known the windows stream through the TMA kernel
+        assert K.lib.last_algo() == ("tma" if extents else "tiled")
+        pick = list(range(min(6, kept))) + list(range(max(kept - 6, 0), kept))      # first and last windows (scene edges)
+        for n in pick:
+            i, j = ij[n]
             p = masked[:, i * 128:i * 128 + 256, j * 128:j * 128 + 256]
             ref = orc.apply_kernel_degradation(torch.from_numpy(np.ascontiguousarray(p)), torch.from_numpy(kb[2]), 8).numpy()
             check_pixels(lr[n], ref, p, exact_degrade(np.ascontiguousarray(p), kb[2], 8), name=f"window{n}")
