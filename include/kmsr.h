@@ -62,9 +62,12 @@ enum {
 };
 /* algo: kernel selection for kmsr_degrade_* */
 enum {
-    KMSR_ALGO_AUTO = 0,    /* TMA row-streaming kernel when the shape qualifies, else the tiled kernel */
-    KMSR_ALGO_TILED = 1,   /* generic polyphase shared-memory tile kernel (any k, factor, H, W)      */
-    KMSR_ALGO_TMA = 2      /* TMA row-streaming kernel; KMSR_E_UNSUPPORTED if the shape does not qualify */
+    KMSR_ALGO_AUTO = 0,    /* headline TMA kernel, else the generic streaming kernel, else the tiled kernel */
+    KMSR_ALGO_TILED = 1,   /* polyphase shared-memory tile kernel (any k, factor, H, W, pad / down mode)   */
+    KMSR_ALGO_TMA = 2,     /* headline TMA row-streaming kernel (k = 13, factor 8, W = 256); KMSR_E_UNSUPPORTED
+                              if the shape does not qualify                                                */
+    KMSR_ALGO_STREAM = 3   /* generic TMA row-streaming kernel (k in 11/13/15/21/31, factor 2/4/8, box mean,
+                              W in 64/128/256*m); KMSR_E_UNSUPPORTED otherwise                             */
 };
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -210,7 +213,7 @@ KMSR_API int kmsr_keep_mask(const float* masked, int C, int H, int W, int P, int
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------
  * Launch counter: number of kernels this library launched on the calling process since load.   */
 KMSR_API int64_t kmsr_launch_count(void);
-/* Name of the kernel the last kmsr_degrade_* call on this thread selected ("tiled" | "tma"). */
+/* Name of the kernel the last kmsr_degrade_* call on this thread selected ("tiled" | "tma" | "stream"). */
 KMSR_API const char* kmsr_last_algo(void);
 
 #ifdef __cplusplus

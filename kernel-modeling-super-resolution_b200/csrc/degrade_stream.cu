@@ -1,0 +1,479 @@
+// degrade_stream.cu -- generic TMA row-streaming fused blur + box-mean downsample + noise kernel.
+//
+// The sweep shapes of BASELINE config 5 (kernel 11..31, patch 64..512, factor 2/4/8) and every other
+// box-mean call with an odd kernel that the headline kernel (degrade_tma.cu: k = 13, factor 8, W = 256)
+// does not take.  Same arithmetic (C_30apply_kernel_to_landsat.py:68-124 with the box mean folded
+// into a stride-S composite kernel, E_make_train_data.py:72-74 / train_gemini.py:137 noise in the
+// epilogue), same data movement idea, parameterised by <K, S>:
+//
+//  * a band (or a 256-column block of a wider band) is a *stream*: its rows cross HBM -> SMEM exactly
+//    once, S rows per TMA tile (cp.async.bulk.tensor, producer thread per stream or per two streams,
+//    full/empty mbarriers, ring of D tiles).  Tiles hold image rows only; the replicate halo is made by
+//    clamping row addresses (top / bottom) and substituting registers (left / right).
+//  * lane = (ly, gx): ly = input row within the tile (S rows), gx = group of 4 adjacent LR columns
+//    (32/S groups per warp, 128 input columns per warp whatever S is).  At step i a lane holds padded
+//    row S*i + ly, which meets output rows i - q through composite rows u = ly + S*q, q < Q =
+//    ceil(KW/S): Q accumulator sets per lane, rotated by value; the oldest one completes each step, is
+//    reduce-scattered over the S row lanes by shuffles and written with the noise term.
+//  * composite-kernel rows come from shared memory (a per-warp copy with an odd 16-byte pitch: the S
+//    distinct rows a warp reads at once never collide); pixels are pivot-shifted and multiplied as
+//    packed FFMA2 pairs exactly like the headline kernel.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tma_util.cuh"
+
+namespace kmsr {
+
+namespace {
+
+constexpr int kConsumers = 8;                  // consumer warps per CTA
+constexpr int kProducers = 4;                  // producer warps (one elected thread each)
+constexpr int kThreadsS = (kConsumers + kProducers) * 32;
+constexpr int kTX = 4;                         // LR columns per lane
+
+template <int K, int S>
+struct Cfg {
+    static constexpr int KW = K + S - 1;                         // composite taps per row / column
+    static constexpr int PAD = K / 2;
+    static constexpr int Q = (KW + S - 1) / S;                   // live output rows per lane
+    static constexpr int GW = kTX * S;                           // input columns per lane group
+    static constexpr int GX = 32 / S;                            // groups per warp
+    static constexpr int AL = (PAD + 3) / 4 * 4;                 // staged columns left of the block (16-byte aligned)
+    static constexpr int SKEW = AL - PAD;                        // first needed float of a lane's aligned segment
+    static constexpr int SEG = KW + (kTX - 1) * S;               // floats a lane needs per row
+    static constexpr int LOADF = (SKEW + SEG + 3) / 4 * 4;       // floats it loads (LDS.128 granules)
+    static constexpr int NP = SEG / 2;                           // pixel pairs (SEG is even: K odd, S even)
+    static constexpr int TP = KW / 2;                            // tap pairs
+    static constexpr int WP = ((KW + 3) / 4 * 4 / 4) % 2 ? (KW + 3) / 4 * 4 : (KW + 3) / 4 * 4 + 4;   // weight row pitch, /4 odd
+    static constexpr int WROWS = Q * S;                          // rows >= KW are zero
+    static_assert(K % 2 == 1 && (S == 2 || S == 4 || S == 8), "odd kernel, factor 2/4/8");
+};
+
+struct StreamArgs {
+    const float* comp;      // [nK, C, KW, KWp]
+    int compPitch;          // KWp
+    const float* dsum;
+    const int* kidx;
+    const float* sigma;
+    const float* pool;
+    const int* nidx;
+    float* lr;
+    long long nitems;       // bands * nblk
+    int C, H, W, Ho, Wo;
+    int nblk;               // column blocks per band (W / BW)
+    int BW;                 // block width in pixels (<= 256)
+    int ng;                 // lane groups per block row (BW / GW)
+    int nw;                 // consumer warps per stream (1 or 2)
+    int ns;                 // streams per CTA (kConsumers / nw)
+    int depth;              // ring slots per stream
+    int pitchF;             // floats per staged row
+    int chunkBytes;         // S * pitchF * 4 (what one TMA tile delivers)
+    int slotBytes;          // chunkBytes rounded up to 128 (TMA destinations are 128-byte aligned)
+    int nchunks;            // H / S
+    int pad_mode, noise_mode;
+    unsigned ringOff, barOff, wOff;
+};
+
+template <int K, int S>
+__global__ void __launch_bounds__(kThreadsS, 1)
+degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a) {
+    using G = Cfg<K, S>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = a.depth;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + a.barOff);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + a.ns * D);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.ns * D; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, a.nw);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long GS = (long long)gridDim.x * a.ns;        // streams in the grid
+
+    if (warp >= kConsumers) {
+        // ============ producers: warp kConsumers + p feeds streams p, p + 4, ... of this CTA ============
+        if (lane != 0) return;
+        const int p = warp - kConsumers;
+        const int nmine = (a.ns - p + kProducers - 1) / kProducers;          // 0, 1 or 2 streams
+        if (nmine <= 0) return;
+        long long item[2], pn[2];
+        int chunk[2], slot[2], pc[2], px[2];
+        uint32_t par[2];
+        auto locate = [&](int j) {               // item -> (patch, band, column block)
+            if (item[j] >= a.nitems) return;
+            const long long band = item[j] / a.nblk;
+            px[j] = ((int)(item[j] - band * a.nblk) * a.BW - G::AL) / 2;
+            pn[j] = band / a.C;
+            pc[j] = (int)(band - pn[j] * a.C);
+        };
+        for (int j = 0; j < 2; ++j) {
+            item[j] = (long long)blockIdx.x * a.ns + p + j * kProducers;
+            if (j >= nmine) item[j] = a.nitems;
+            chunk[j] = 0; slot[j] = 0; par[j] = 1; pn[j] = 0; pc[j] = 0; px[j] = 0;
+            locate(j);
+        }
+        const uint64_t policy = l2_evict_first_policy();
+        bool active = true;
+        while (active) {
+            active = false;
+            for (int j = 0; j < 2; ++j) {
+                if (item[j] >= a.nitems) continue;
+                active = true;
+                const int s = p + j * kProducers;
+                const uint32_t sfull = full0 + 8 * (s * D + slot[j]), sempty = empty0 + 8 * (s * D + slot[j]);
+                mbar_wait_relaxed(sempty, par[j]);
+                mbar_arrive_expect_tx(sfull, a.chunkBytes);
+                tma_load_4d_hint(smem_u32(smem_raw + a.ringOff + (size_t)(s * D + slot[j]) * a.slotBytes), &tmap, px[j],
+                                 S * chunk[j], pc[j], (int)pn[j], sfull, policy);
+                if (++slot[j] == D) { slot[j] = 0; par[j] ^= 1; }
+                if (++chunk[j] == a.nchunks) { chunk[j] = 0; item[j] += GS; locate(j); }
+            }
+        }
+        return;
+    }
+
+    // ======================================= consumers =======================================
+    const int s = warp / a.nw, wq = warp - s * a.nw;          // stream, warp within the stream
+    const int ly = lane & (S - 1), gx = lane / S;
+    const int g_raw = wq * G::GX + gx;                        // lane group within the block row
+    const bool lane_on = g_raw < a.ng;                        // W = 64: half of the groups have no columns
+    const int g = lane_on ? g_raw : a.ng - 1;
+    const unsigned char* sring = smem_raw + a.ringOff + (size_t)s * D * a.slotBytes;
+    const uint32_t sfull = full0 + 8 * s * D, sempty = empty0 + 8 * s * D;
+    float* wsm = reinterpret_cast<float*>(smem_raw + a.wOff) + (size_t)warp * G::WROWS * G::WP;
+    const bool replicate = a.pad_mode == KMSR_PAD_REPLICATE;
+    const bool noisy = a.noise_mode != KMSR_NOISE_NONE;
+    const long long ohw = (long long)a.Ho * a.Wo;
+    const int nsteps = a.Ho + G::Q - 1;
+
+    // ring bookkeeping: chunks of this stream are numbered continuously across its items
+    int wslot = 0, rslot = 0;          // next slot to wait for / to release
+    uint32_t wpar = 0;
+    long long waited = 0, released = 0;   // chunk counters (global within the stream)
+
+    for (int r = lane; r < G::WROWS * G::WP; r += 32) wsm[r] = 0.0f;       // rows >= KW and pitch padding stay zero
+    __syncwarp();
+
+    long long base = 0;                // chunk counter of the current item's first chunk
+    for (long long item = (long long)blockIdx.x * a.ns + s; item < a.nitems; item += GS, base += a.nchunks) {
+        const long long band = item / a.nblk;
+        const int blk = (int)(item - band * a.nblk);
+        const long long n = band / a.C;
+        const int c = (int)(band - n * a.C);
+        const int kid = a.kidx ? __ldg(a.kidx + n) : 0;
+        const bool edge_l = replicate && blk == 0, edge_r = replicate && blk == a.nblk - 1;
+
+        // composite kernel of this band -> the warp's weight copy (pitch WP, rows >= KW zero)
+        {
+            const float* kc = a.comp + ((long long)kid * a.C + c) * (G::KW * a.compPitch);
+            __syncwarp();
+            for (int e = lane; e < G::KW * G::KW; e += 32) {
+                const int u = e / G::KW, v = e - u * G::KW;
+                wsm[u * G::WP + v] = __ldg(kc + u * a.compPitch + v);
+            }
+            __syncwarp();
+        }
+        const float ds = __ldg(a.dsum + (long long)kid * a.C + c);
+        float scale = 1.0f;
+        const float* nz = nullptr;
+        if (noisy) {
+            nz = a.pool + ((long long)__ldg(a.nidx + n) * a.C + c) * ohw;
+            if (a.noise_mode == KMSR_NOISE_SIGMA) scale = __ldg(a.sigma + (long long)kid * a.C + c);
+        }
+
+        u64 A[G::Q][kTX];
+#pragma unroll
+        for (int q = 0; q < G::Q; ++q)
+#pragma unroll
+            for (int x = 0; x < kTX; ++x) A[q][x] = 0ull;
+        float pv = 0.0f;
+        u64 npv2 = 0ull;
+
+        // output columns after the reduce-scatter over the S row lanes
+        const int col0 = blk * (a.BW / S) + kTX * g;          // first LR column of this lane group
+        const int ox = S == 8 ? (ly >> 1) : (S == 4 ? ly : 2 * ly);
+        const bool writer = lane_on && (S != 8 || (ly & 1) == 0);
+
+#pragma unroll 1
+        for (int i = 0; i < nsteps; ++i) {
+            // ---- rows this step needs: padded rows S*i .. S*i+S-1 = image rows S*i - PAD + ly ----
+            const int rr_raw = S * i + ly - G::PAD;
+            const int rr = min(max(rr_raw, 0), a.H - 1);
+            const bool row_ok = rr_raw >= 0 && rr_raw < a.H;               // zero padding: rows outside are zeros
+            const int hi_chunk = min(max(S * i + S - 1 - G::PAD, 0), a.H - 1) / S;
+            while (waited <= base + hi_chunk) {
+                mbar_wait(sfull + 8 * wslot, wpar);
+                if (++wslot == D) { wslot = 0; wpar ^= 1; }
+                ++waited;
+            }
+            const long long ck = base + rr / S;                             // chunk of this lane's row
+            const int slot = (int)(ck % D);
+            const float* src = reinterpret_cast<const float*>(sring + (size_t)slot * a.slotBytes) +
+                               (rr % S) * a.pitchF + G::GW * g;
+            if (i == 0) {
+                // pivot: pixel (0, first column of the lane group) -- row 0 is in the item's first chunk
+                const int s0 = (int)(base % D);
+                pv = reinterpret_cast<const float*>(sring + (size_t)s0 * a.slotBytes)[G::AL + G::GW * g];
+                if (!isfinite(pv)) pv = 0.0f;
+                npv2 = pack2(-pv, -pv);
+            }
+            float e[G::LOADF];
+#pragma unroll
+            for (int j = 0; j < G::LOADF / 4; ++j) {
+                const float4 t = reinterpret_cast<const float4*>(src)[j];
+                e[4 * j + 0] = t.x; e[4 * j + 1] = t.y; e[4 * j + 2] = t.z; e[4 * j + 3] = t.w;
+            }
+            // release the chunks no later step needs (all of them after the item's last step)
+            {
+                const long long lo_next = i + 1 < nsteps ? base + min(max(S * (i + 1) - G::PAD, 0), a.H - 1) / S
+                                                          : base + a.nchunks;
+                __syncwarp();
+                while (released < lo_next) {
+                    if (lane == 0) mbar_arrive(sempty + 8 * rslot);
+                    if (++rslot == D) rslot = 0;
+                    ++released;
+                }
+            }
+            // noise of the row that completes in this step: issue the load before the arithmetic
+            const int Y = i - (G::Q - 1);
+            float nzv[2] = {0.0f, 0.0f};
+            if (noisy && writer && Y >= 0) {
+                const float* np_ = nz + (long long)Y * a.Wo + col0 + ox;
+                nzv[0] = __ldg(np_);
+                if (S == 2) nzv[1] = __ldg(np_ + 1);
+            }
+
+            // d[j] = pixel column GW*g - PAD + j of the block, j < SEG
+            float d[G::SEG];
+#pragma unroll
+            for (int j = 0; j < G::SEG; ++j) d[j] = e[j + G::SKEW];
+            if (!replicate && !row_ok) {
+#pragma unroll
+                for (int j = 0; j < G::SEG; ++j) d[j] = 0.0f;
+            }
+            if (edge_l) {
+                // columns < 0 of the image take pixel 0: group gg has PAD - GW*gg of them
+#pragma unroll
+                for (int gg = 0; gg * G::GW < G::PAD; ++gg) {
+                    if (g == gg) {
+                        const int hl = G::PAD - G::GW * gg;
+#pragma unroll
+                        for (int j = 0; j < G::SEG; ++j)
+                            if (j < hl) d[j] = d[hl < G::SEG ? hl : G::SEG - 1];
+                    }
+                }
+            }
+            if (edge_r) {
+                // columns >= W take pixel W-1: the group gg from the right end sees column W at d[PAD + GW*(gg+1)]
+#pragma unroll
+                for (int gg = 0; G::PAD + G::GW * (gg + 1) < G::SEG; ++gg) {
+                    if (g == a.ng - 1 - gg) {
+                        const int hr = G::PAD + G::GW * (gg + 1);
+#pragma unroll
+                        for (int j = 0; j < G::SEG; ++j)
+                            if (j >= hr) d[j] = d[hr - 1];
+                    }
+                }
+            }
+            u64 P[G::NP];
+#pragma unroll
+            for (int m = 0; m < G::NP; ++m) P[m] = add2(pack2(d[2 * m], d[2 * m + 1]), npv2);
+
+            // ---- multiply-accumulate: composite row u = ly + S*q meets output row i - q ----
+#pragma unroll
+            for (int q = 0; q < G::Q; ++q) {
+                const int u = ly + S * q;
+                const float* wrow = wsm + u * G::WP;
+                u64 T[kTX];
+#pragma unroll
+                for (int x = 0; x < kTX; ++x) T[x] = A[q][x];
+#pragma unroll
+                for (int t4 = 0; t4 < (G::TP + 1) / 2; ++t4) {
+                    const ulonglong2 w2 = reinterpret_cast<const ulonglong2*>(wrow)[t4];
+#pragma unroll
+                    for (int x = 0; x < kTX; ++x) {
+                        T[x] = fma2(w2.x, P[(S * x) / 2 + 2 * t4], T[x]);
+                        if (2 * t4 + 1 < G::TP) T[x] = fma2(w2.y, P[(S * x) / 2 + 2 * t4 + 1], T[x]);
+                    }
+                }
+                // a row below the window (u >= KW) must not even add 0 * pixel: a NaN there would poison an
+                // output the reference keeps
+                const bool live = (q + 1) * S <= G::KW || u < G::KW;
+#pragma unroll
+                for (int x = 0; x < kTX; ++x) if (live) A[q][x] = T[x];
+            }
+
+            // ---- the oldest set completes: reduce over the S row lanes, epilogue, store ----
+            if (Y >= 0) {
+                float v[kTX];
+#pragma unroll
+                for (int x = 0; x < kTX; ++x) v[x] = lo2(A[G::Q - 1][x]) + hi2(A[G::Q - 1][x]);
+                float r0, r1 = 0.0f;
+                {
+                    const bool up = (ly & (S / 2)) != 0;
+                    float k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];
+                    const float s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
+                    k0 += __shfl_xor_sync(0xffffffffu, s0, S / 2);
+                    k1 += __shfl_xor_sync(0xffffffffu, s1, S / 2);
+                    r0 = k0; r1 = k1;
+                }
+                if (S >= 4) {
+                    const bool up = (ly & (S / 4)) != 0;
+                    float k = up ? r1 : r0;
+                    const float sx = up ? r0 : r1;
+                    k += __shfl_xor_sync(0xffffffffu, sx, S / 4);
+                    r0 = k;
+                }
+                if (S == 8) r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+                if (writer) {
+                    float* out = a.lr + band * ohw + (long long)Y * a.Wo + col0 + ox;
+                    float res = pv + fmaf(pv, ds, r0);
+                    if (noisy) res = fmaf(scale, nzv[0], res);
+                    out[0] = res;
+                    if (S == 2) {
+                        float res1 = pv + fmaf(pv, ds, r1);
+                        if (noisy) res1 = fmaf(scale, nzv[1], res1);
+                        out[1] = res1;
+                    }
+                }
+            }
+            // rotate the accumulator sets by value: set q becomes set q + 1, set 0 starts empty
+#pragma unroll
+            for (int q = G::Q - 1; q > 0; --q)
+#pragma unroll
+                for (int x = 0; x < kTX; ++x) A[q][x] = A[q - 1][x];
+#pragma unroll
+            for (int x = 0; x < kTX; ++x) A[0][x] = 0ull;
+        }
+    }
+}
+
+template <int K, int S>
+int launch_kS(const CUtensorMap& tmap, StreamArgs& t, int sms, cudaStream_t st) {
+    using G = Cfg<K, S>;
+    // row pitch: AL | BW | right extent of the last group, 16-byte granules, odd count
+    const int right = G::LOADF - G::GW - G::AL;
+    int pitch = G::AL + t.BW + (right > 0 ? right : 0);
+    pitch = (pitch + 3) / 4 * 4;
+    if ((pitch / 4) % 2 == 0) pitch += 4;
+    t.pitchF = pitch;
+    t.chunkBytes = S * pitch * 4;
+    t.slotBytes = (t.chunkBytes + 127) / 128 * 128;
+    t.nchunks = t.H / S;
+    t.ng = t.BW / G::GW;
+    const size_t wbytes = (size_t)kConsumers * G::WROWS * G::WP * 4;
+    int dev = 0, max_smem = 0;
+    KMSR_CUDA_OK(cudaGetDevice(&dev));
+    KMSR_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t fixed = wbytes + 2 * 8 * 8 * 16 + 1024;
+    int depth = (int)(((size_t)max_smem - fixed) / ((size_t)t.ns * t.slotBytes));
+    // a ring must at least hold the rows one step touches plus one tile in flight
+    const int need = 3;
+    if (depth > 16) depth = 16;
+    KMSR_REQUIRE(depth >= need, KMSR_E_UNSUPPORTED, "degrade (stream): k=%d factor=%d W=%d does not fit shared memory", K, S, t.W);
+    t.depth = depth;
+    // chunk size must be a multiple of 128 B for the tile base alignment
+    t.ringOff = 0;
+    size_t ring = (size_t)t.ns * depth * t.slotBytes;
+    ring = (ring + 127) / 128 * 128;
+    t.barOff = (unsigned)ring;
+    t.wOff = (unsigned)(ring + ((2 * t.ns * depth * 8 + 127) / 128) * 128);
+    const size_t smem = t.wOff + wbytes;
+    auto kern = degrade_stream_kernel<K, S>;
+    KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = (t.nitems + t.ns - 1) / t.ns;
+    if (grid > sms) grid = sms;
+    kern<<<(unsigned)grid, kThreadsS, smem, st>>>(tmap, t);
+    KMSR_LAUNCH_CHECK("degrade_stream_kernel");
+    return KMSR_OK;
+}
+
+template <int K>
+int launch_k(const CUtensorMap& tmap, StreamArgs& t, int S, int sms, cudaStream_t st) {
+    switch (S) {
+        case 2: return launch_kS<K, 2>(tmap, t, sms, st);
+        case 4: return launch_kS<K, 4>(tmap, t, sms, st);
+        default: return launch_kS<K, 8>(tmap, t, sms, st);
+    }
+}
+
+bool k_supported(int k) { return k == 11 || k == 13 || k == 15 || k == 21 || k == 31; }
+
+}  // namespace
+
+bool stream_shape_ok(const DegradeArgs& a, int down_mode, const char** why) {
+    const Geometry& g = a.g;
+    *why = "";
+    if (down_mode != KMSR_DOWN_BOXMEAN) { *why = "box-mean downsampling only"; return false; }
+    if (g.kh != g.kw || !k_supported(g.kh)) { *why = "square kernels of size 11, 13, 15, 21, 31"; return false; }
+    const int S = g.stride;
+    if (S != 2 && S != 4 && S != 8) { *why = "factor 2, 4 or 8"; return false; }
+    if (a.patch_offsets) { *why = "scene windows not covered"; return false; }
+    if (a.W != 64 && a.W != 128 && (a.W % 256 != 0 || a.W > 4096)) { *why = "W in {64, 128, 256*m}"; return false; }
+    if (a.H < S || a.H % S != 0) { *why = "H a multiple of the factor"; return false; }
+    if (a.H / S + (g.KW + S - 1) / S - 1 < 1) { *why = "empty output"; return false; }
+    if (((uintptr_t)a.hr & 15) || (a.sH & 3) || (a.sC & 3) || (a.N > 1 && (a.sN & 3))) {
+        *why = "HR base / strides not 16-byte aligned"; return false;
+    }
+    if (a.sH < a.W || a.sC < 1 || (a.N > 1 && a.sN < 1)) { *why = "non-positive strides"; return false; }
+    if (a.N >= (1ll << 31) || a.N * a.C >= (1ll << 38)) { *why = "too many patches"; return false; }
+    return true;
+}
+
+int launch_degrade_stream(const DegradeArgs& a, cudaStream_t st) {
+    EncodeTiledFn enc = get_tensor_map_encoder();
+    KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "degrade (stream): cuTensorMapEncodeTiled is not available from the driver");
+    const Geometry& g = a.g;
+    const int S = g.stride, K = g.kh;
+    StreamArgs t;
+    t.comp = a.comp; t.compPitch = g.KWp; t.dsum = a.dsum; t.kidx = a.kidx; t.sigma = a.sigma; t.pool = a.pool;
+    t.nidx = a.nidx; t.lr = a.lr;
+    t.C = a.C; t.H = a.H; t.W = a.W; t.Ho = g.Ho; t.Wo = g.Wo;
+    t.BW = a.W >= 256 ? 256 : a.W;
+    t.nblk = a.W / t.BW;
+    t.nw = t.BW == 256 ? 2 : 1;
+    t.ns = kConsumers / t.nw;
+    t.nitems = a.N * a.C * t.nblk;
+    t.pad_mode = a.pad_mode; t.noise_mode = a.noise_mode;
+
+    // staged row: pitch floats starting AL columns left of the block; pitch is fixed by <K, S> and BW
+    int AL = (K / 2 + 3) / 4 * 4;
+    const int KW = K + S - 1;
+    const int SEG = KW + 3 * S, SKEW = AL - K / 2;
+    const int LOADF = (SKEW + SEG + 3) / 4 * 4;
+    const int right = LOADF - 4 * S - AL;
+    int pitch = AL + t.BW + (right > 0 ? right : 0);
+    pitch = (pitch + 3) / 4 * 4;
+    if ((pitch / 4) % 2 == 0) pitch += 4;
+    KMSR_REQUIRE(pitch / 2 <= 256, KMSR_E_UNSUPPORTED, "degrade (stream): staged row of %d floats exceeds the TMA box limit", pitch);
+
+    CUtensorMap tmap;
+    cuuint64_t gdim[4] = {(cuuint64_t)(a.W / 2), (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.N};
+    const long long sN = a.N > 1 ? a.sN : (long long)a.C * a.sC;
+    cuuint64_t gstr[3] = {(cuuint64_t)a.sH * 4, (cuuint64_t)a.sC * 4, (cuuint64_t)sN * 4};
+    cuuint32_t box[4] = {(cuuint32_t)(pitch / 2), (cuuint32_t)S, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)a.hr, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "degrade (stream): cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+
+    int dev = 0, sms = 0;
+    KMSR_CUDA_OK(cudaGetDevice(&dev));
+    KMSR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    set_algo("stream");
+    switch (K) {
+        case 11: return launch_k<11>(tmap, t, S, sms, st);
+        case 13: return launch_k<13>(tmap, t, S, sms, st);
+        case 15: return launch_k<15>(tmap, t, S, sms, st);
+        case 21: return launch_k<21>(tmap, t, S, sms, st);
+        default: return launch_k<31>(tmap, t, S, sms, st);
+    }
+}
+
+}  // namespace kmsr

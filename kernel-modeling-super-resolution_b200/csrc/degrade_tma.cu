@@ -36,6 +36,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tma_util.cuh"
 
 namespace kmsr {
 
@@ -81,99 +82,6 @@ struct TmaArgs {
     long long sH;            // scene row stride in elements (windows only)
     double* stat_part;       // STATS: [nbands][2 warps][sum x, sum x^2] (data_mean_std.py:32-33 fused), else nullptr
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-// Producer-side wait: same test, but the thread may stay suspended for up to ~1 us per probe instead of
-// re-issuing try_wait + branch every ~100 cycles (four spinning producers took 54 % of all issued
-// instructions in the r16 ncu capture); an arrive still wakes it immediately.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP_R:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONE_R;\n\t"
-        "bra WAIT_LOOP_R;\n\t"
-        "DONE_R:\n\t"
-        "}" ::"r"(bar), "r"(parity), "r"(1000u) : "memory");
-}
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, int w,
-                                            uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(bar)
-        : "memory");
-}
-// HR pixels are read exactly once: evict-first keeps them from flushing the 84 MB noise pool and the
-// composite bank out of the 126 MB L2.
-__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* map, int x, int y, int z, int w,
-                                                 uint32_t bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(bar),
-        "l"(policy)
-        : "memory");
-}
-
-// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): one issue slot, two IEEE fp32 results ----
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pack2(float lo, float hi) {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float lo2(u64 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return a;
-}
-__device__ __forceinline__ float hi2(u64 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return b;
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-    u64 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 
 constexpr int kTapPairs = kKW / 2;             // 10 (even, odd) tap pairs per composite row
 constexpr int kLoadP = kLoadF / 2;             // 24 pixel pairs per lane and step
@@ -586,22 +494,6 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
 }  // namespace
 
 bool tma_shape_ok(const DegradeArgs& a, const char** why) {
@@ -625,7 +517,7 @@ bool tma_shape_ok(const DegradeArgs& a, const char** why) {
 }
 
 int launch_degrade_tma(const DegradeArgs& a, cudaStream_t st) {
-    EncodeTiledFn enc = get_encode();
+    EncodeTiledFn enc = get_tensor_map_encoder();
     KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "degrade (tma): cuTensorMapEncodeTiled is not available from the driver");
     CUtensorMap tmap;
     // [N, C, H, W/2] of 64-bit elements; box = 138 x 8 x 1 x 1 (x starts at -4: zero-filled halo).

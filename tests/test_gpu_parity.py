@@ -295,6 +295,51 @@ def test_scene_windows_degrade_like_cut_patches(K, golden, synth, bank):
             check_pixels(lr[n], ref, p, exact_degrade(np.ascontiguousarray(p), kb[2], 8), name=f"window{n}")
 
 
+@pytest.mark.parametrize("k,s,p", [(11, 8, 64), (13, 4, 128), (15, 2, 64), (21, 8, 256), (31, 4, 128), (31, 8, 512),
+                                   (13, 8, 128), (21, 2, 128), (31, 2, 64), (11, 4, 512), (15, 8, 256), (13, 2, 256)])
+def test_generic_streaming_kernel(K, synth, k, s, p):
+    """degrade_stream<K, S> (BASELINE config 5 shapes): replicate and zero padding, noise epilogue, NaN footprint,
+    against the reference call sites; bit-identical to itself under sharding."""
+    n = 3
+    kern = synth.softmax_kernels(k, 7 + k)
+    hr = np.concatenate([synth.make_hr(2, 2000 + k + s, "textured", size=p), synth.make_hr(1, 2100 + k, "water", size=p)])
+    hd = torch.from_numpy(hr).cuda()
+    kd = torch.from_numpy(kern).cuda()
+    lr = K.ops.degrade_batch(hd, kd, factor=s, algo="stream").cpu().numpy()
+    assert K.lib.last_algo() == "stream"
+    for i in range(n):
+        ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kern), s).numpy()
+        check_pixels(lr[i], ref, hr[i], exact_degrade(hr[i], kern, s), name=f"stream k{k} s{s} p{p} #{i}")
+    # zero padding (train_gemini.py:128) + sigma noise
+    ho = p // s
+    pool = (np.random.RandomState(3).standard_normal((5, 5, ho, ho)) * 0.5).astype(np.float32)
+    sig = np.linspace(0.7, 1.0, 5, dtype=np.float32)[None]
+    nidx = np.array([4, 0, 2], dtype=np.int32)
+    lz = K.ops.degrade_batch(hd, kd, factor=s, pad_mode="zero", sigma=torch.from_numpy(sig), pool=torch.from_numpy(pool).cuda(),
+                             nidx=nidx, noise_mode="sigma", algo="stream").cpu().numpy()
+    lt = K.ops.degrade_batch(hd, kd, factor=s, pad_mode="zero", sigma=torch.from_numpy(sig), pool=torch.from_numpy(pool).cuda(),
+                             nidx=nidx, noise_mode="sigma", algo="tiled").cpu().numpy()
+    # zero padding + box mean is not a reference combination: held to the exact (fp64) value and to the tiled kernel
+    for i in range(n):
+        rngs = orc.band_range(hr[i])
+        ex = exact_degrade(hr[i], kern, s, zero_pad=True) + sig[0][:, None, None].astype(np.float64) * pool[nidx[i]]
+        slack = np.spacing(np.abs(ex).astype(np.float32)).astype(np.float64) / rngs
+        # with zeros mixed into a level-80 / range-2 patch the border sums live at the radiance level, not at the
+        # patch's dynamic range: the water patch gets the level-scaled bar there
+        tol = 5e-6 if i < 2 else 5e-6 * float(np.abs(hr[i]).max()) / float(rngs.min())
+        assert (np.abs(lz[i] - ex) / rngs <= tol + slack).all(), (k, s, p, i, float((np.abs(lz[i] - ex) / rngs).max()))
+        assert (np.abs(lz[i].astype(np.float64) - lt[i]) / rngs <= 2e-4 + slack).all()      # sanity against the other kernel
+    # NaN footprint
+    hn = hr.copy()
+    hn[0, 1, 0, 0] = np.nan
+    hn[1, 3, p // 2, p // 3] = np.nan
+    hn[2, 0, p - 1, p - 1] = np.nan
+    ln = K.ops.degrade_batch(torch.from_numpy(hn).cuda(), kd, factor=s, algo="stream").cpu().numpy()
+    for i in range(n):
+        ref = orc.apply_kernel_degradation(torch.from_numpy(hn[i]), torch.from_numpy(kern), s).numpy()
+        assert np.array_equal(np.isnan(ln[i]), np.isnan(ref)), (k, s, p, i)
+
+
 def test_nan_propagation_matches_reference(K, synth, bank):
     """A NaN pixel poisons exactly the LR pixels whose (clamped) window contains it."""
     kb, _ = bank
