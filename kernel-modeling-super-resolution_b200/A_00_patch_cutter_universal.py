@@ -3,15 +3,19 @@
 `apply_water_mask` keeps the reference signature and its in-place side effect (-9999 -> NaN on the
 argument, CUT:102).  `patch_grid_keep` is the CUT:152-183 raster loop as two kernels (NaN count per
 stride cell, then per window) and returns the keep mask; `create_patches` yields the kept windows
-in raster (i, j) order -- as zero-copy device views -- without writing NetCDF (writer: SURVEY 8f).
+in raster (i, j) order -- as zero-copy device views; `create_patches_nc` adds the reference's writer loop
+(CUT:126-197) on top of it through patch_io.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, patch_io
 
+BAND_NAMES = ["L_TOA_443", "L_TOA_490", "L_TOA_555", "L_TOA_660", "L_TOA_865"]   # CUT:34
 PATCH_SIZE = 256            # CUT:29
 STRIDE_RATIO = 0.5          # CUT:30
 NAN_THRESHOLD = 0.0         # CUT:31
@@ -68,3 +72,41 @@ def create_patches(data, patch_size: int = PATCH_SIZE, stride_ratio: float = STR
     ij = torch.nonzero(keep)                                  # raster order == reference loop order
     offsets = (ij[:, 0] * stride * w + ij[:, 1] * stride).to(torch.int64)
     return total, int(ij.shape[0]), ij.cpu().numpy(), offsets, scene
+
+
+def save_patch_as_nc(patch: np.ndarray, output_path: str, metadata: dict, grid_i: int, grid_j: int, h_offset: int,
+                     w_offset: int) -> None:
+    """CUT:200-260: one patch file with groups geophysical_data (one variable per band) and navigation_data
+    (2-D navigation arrays cropped to the patch window) plus the grid attributes."""
+    band_names = metadata.get("band_names", BAND_NAMES)
+    _, h, w = patch.shape
+    groups = {"geophysical_data": {b: patch[i] for i, b in enumerate(band_names)}}
+    nav = metadata.get("navigation_data", {})
+    if nav:
+        groups["navigation_data"] = {k: v[h_offset:h_offset + h, w_offset:w_offset + w] for k, v in nav.items()
+                                     if getattr(v, "ndim", 0) == 2}
+    attrs = {"source_file": metadata.get("source_file", "unknown"), "invalid_value": metadata.get("invalid_value", INVALID_VALUE),
+             "grid_i": grid_i, "grid_j": grid_j, "h_offset": h_offset, "w_offset": w_offset, "patch_size": h,
+             "description": "Patch extracted from Landsat/GOCI-2 L1B data"}
+    patch_io.write_groups(output_path, groups, attrs)
+
+
+def create_patches_nc(data: np.ndarray, patch_size: int, stride_ratio: float, nan_threshold: float, output_dir: str,
+                      prefix: str, metadata: dict, ext: str = ".nc"):
+    """CUT:126-197: tile `data` [C,H,W] (stride = int(patch_size * stride_ratio)), keep a window iff its NaN ratio is
+    <= nan_threshold, write `<prefix>_<i:03d>_<j:03d><ext>` per kept window in raster order; returns (total, kept).
+    The NaN census of all windows is one GPU pass (ops.keep_mask); only kept windows are copied out and written."""
+    total, kept, ij, _, scene = create_patches(data, patch_size, stride_ratio, nan_threshold)
+    _, h, w = scene.shape
+    hp, wp, stride = patch_grid(h, w, patch_size, stride_ratio)
+    print(f"  data size: {tuple(scene.shape)}")
+    print(f"  patch size: {patch_size}x{patch_size}, stride: {stride} ({int(stride_ratio * 100)}% overlap)")
+    print(f"  patch grid: {hp}x{wp} = {hp * wp}")
+    os.makedirs(output_dir, exist_ok=True)
+    host = data if isinstance(data, np.ndarray) else scene.cpu().numpy()
+    for i, j in ij:
+        hs, ws = int(i) * stride, int(j) * stride
+        save_patch_as_nc(host[:, hs:hs + patch_size, ws:ws + patch_size], os.path.join(output_dir, f"{prefix}_{int(i):03d}_{int(j):03d}{ext}"),
+                         metadata, int(i), int(j), hs, ws)
+    print(f"  generated: {total} windows, kept: {kept} (dropped {total - kept}), saved to {output_dir}")
+    return total, kept

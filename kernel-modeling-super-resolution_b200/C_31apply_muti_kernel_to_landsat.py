@@ -13,8 +13,8 @@ import os
 import numpy as np
 import torch
 
-from . import ops, rng
-from .C_30apply_kernel_to_landsat import BAND_NAMES, _apply  # noqa: F401
+from . import ops, patch_io, rng
+from .C_30apply_kernel_to_landsat import BAND_NAMES, _apply, _degrade_files  # noqa: F401
 
 
 def load_kernel(kernel_path: str) -> torch.Tensor:
@@ -60,3 +60,33 @@ def degrade_multi_kernel(patches: torch.Tensor, kernel_bank: torch.Tensor, sigma
                            pool=torch.as_tensor(noise_pool).to(dev), nidx=nidx, factor=int(downscale_factor),
                            pad_mode=pad_mode, down_mode=down_mode, noise_mode=noise_mode)
     return (lr if patches.is_cuda else lr.cpu()), kidx, nidx
+
+
+def load_landsat_nc(nc_path: str):
+    """C_31:40-56: the five bands of group 'hr' as a [C,H,W] float32 tensor + band names."""
+    return torch.from_numpy(patch_io.read_group_bands(nc_path, "hr", BAND_NAMES)), list(BAND_NAMES)
+
+
+def process_landsat_folder(landsat_dir: str, kernel_path: str, output_dir: str, downscale_factor: int = 8,
+                           visualize_top_n: int = 5) -> None:
+    """C_31:136-195: read group 'hr' of every patch file (sorted), write / overwrite group 'lr' IN THE SAME FILE.
+    `visualize_top_n` is accepted for signature compatibility; the QA plots are out of scope."""
+    kernel = load_kernel(kernel_path)
+    names = patch_io.list_patch_files(landsat_dir, sort=True)
+    if len(names) == 0:
+        print(f"no patch files (.nc / .npz) found in {landsat_dir}")
+        return
+    print(f"\nfound {len(names)} Landsat patch files")
+    os.makedirs(output_dir, exist_ok=True)
+    done = 0
+    paths = [os.path.abspath(os.path.join(landsat_dir, f)) for f in names]
+    for pth, img, lr in _degrade_files(paths, kernel, downscale_factor, "hr", True):
+        try:
+            patch_io.add_group(pth, "lr", lr.numpy(), BAND_NAMES, dims=("y_lr", "x_lr"),
+                               history="Added lr group by applying learned blur kernel and downsampling",
+                               long_name="TOA Radiance at {wl} nm (LR)")
+            print(f"degraded: {tuple(img.shape)} -> {tuple(lr.shape)}; updated {pth}")
+            done += 1
+        except Exception as e:  # noqa: BLE001   C_31:185-189
+            print(f"failed: {os.path.basename(pth)}: {e}")
+    print(f"\ndone: {done} of {len(names)} files; kernel {kernel_path}; source {landsat_dir}")

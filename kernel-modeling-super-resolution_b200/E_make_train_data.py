@@ -8,10 +8,12 @@ the intermediate 'blurred' group is lossless f4, so fusing is value-preserving).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
-from . import ops, rng
+from . import ops, patch_io, rng
 
 BAND_NAMES = ["L_TOA_443", "L_TOA_490", "L_TOA_555", "L_TOA_660", "L_TOA_865"]   # E:28
 
@@ -70,3 +72,79 @@ def make_pairs(hr, kernel, noise_pool, seed: int | None = 42, downscale_factor: 
     if with_stats:
         return t, (lr if t.is_cuda else lr.cpu()), nidx, mean, std
     return t, (lr if t.is_cuda else lr.cpu()), nidx
+
+
+def load_group_bands(nc_path: str, group_name: str) -> np.ndarray:
+    """E:31-42."""
+    return patch_io.read_group_bands(nc_path, group_name, BAND_NAMES)
+
+
+def load_navigation_data(nc_path: str) -> dict:
+    """E:45-58."""
+    return patch_io.read_navigation(nc_path)
+
+
+def save_training_sample(output_path: str, hr: np.ndarray, lr: np.ndarray, nav_data: dict):
+    """E:77-117."""
+    patch_io.write_training_sample(output_path, hr, lr, nav_data, BAND_NAMES)
+
+
+def process_files(input_dir: str, noise_pool_path: str, output_dir: str, vis_dir: str = None, max_vis: int = 30,
+                  seed: int = 42, chunk: int = 256):
+    """E:187-272: for every patch file (os.listdir order) read 'denoised' (HR), 'blurred' and navigation data, gate the
+    shapes (a rejected or unreadable file draws nothing, E:239-247), lr = blurred + noise_pool[randint] with the
+    global numpy stream seeded once (E:190, E:72), write `<name>_train.<ext>` with groups hr / lr / navigation_data.
+    The gather + add of a chunk of files is one GPU launch; `vis_dir` / `max_vis` are accepted for signature
+    compatibility (plots are out of scope).  Returns (success_count, fail_count)."""
+    np.random.seed(seed)
+    if not os.path.isdir(input_dir):
+        raise FileNotFoundError(f"input directory does not exist: {input_dir}")
+    if not os.path.isfile(noise_pool_path):
+        raise FileNotFoundError(f"noise pool file does not exist: {noise_pool_path}")
+    noise_pool = np.load(noise_pool_path)
+    print(f"noise pool {noise_pool_path}: {noise_pool.shape}")
+    os.makedirs(output_dir, exist_ok=True)
+    names = patch_io.list_patch_files(input_dir, sort=False)
+    if not names:
+        raise FileNotFoundError(f"no patch files (.nc / .npz) in {input_dir}")
+    ops.require_cuda()
+    pool_dev = _device_pool(noise_pool)
+    ok = fail = 0
+    for a in range(0, len(names), chunk):
+        accepted = []
+        for fname in names[a:a + chunk]:
+            pth = os.path.join(input_dir, fname)
+            try:
+                hr = load_group_bands(pth, "denoised")
+                blurred = load_group_bands(pth, "blurred")
+                nav = load_navigation_data(pth)
+                if hr.shape[1] != 256 or hr.shape[2] != 256:
+                    print(f"\n{fname}: HR shape {hr.shape} is not (5,256,256), skipped")
+                    fail += 1
+                    continue
+                if blurred.shape[1] != 32 or blurred.shape[2] != 32:
+                    print(f"\n{fname}: blurred shape {blurred.shape} is not (5,32,32), skipped")
+                    fail += 1
+                    continue
+                accepted.append((fname, hr, blurred, nav))
+            except Exception as e:  # noqa: BLE001   E:264-267
+                print(f"\nfailed {fname}: {e}")
+                fail += 1
+        if not accepted:
+            continue
+        nidx = rng.draw_noise_indices(len(accepted), len(noise_pool), None)     # continues the stream seeded above
+        b = torch.from_numpy(np.stack([x[2] for x in accepted])).cuda()
+        lr = ops.add_noise_batch(b, pool_dev, nidx).cpu().numpy()
+        for (fname, hr, _, nav), l in zip(accepted, lr):
+            ext = os.path.splitext(fname)[1]
+            base = fname.replace(f"_denoised_blurred{ext}", f"_train{ext}")
+            if base == fname:
+                base = fname.replace(ext, f"_train{ext}")
+            try:
+                save_training_sample(os.path.join(output_dir, base), hr, l, nav)
+                ok += 1
+            except Exception as e:  # noqa: BLE001
+                print(f"\nfailed {fname}: {e}")
+                fail += 1
+    print(f"\ndone: {ok} written, {fail} failed, output {output_dir}")
+    return ok, fail

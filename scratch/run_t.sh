@@ -1,4 +1,5 @@
 #!/bin/bash
 T=${1:-r21}
-timeout 1200 python -m pytest tests -m gpu -x -q ${2:-} > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
+shift
+timeout 1200 python -m pytest tests -m gpu -x -q "$@" > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
 tail -40 gpurun_out/${T}_pytest.log | cut -c1-300

@@ -417,3 +417,106 @@ def test_c_abi_error_codes(K):
     # empty batch is a no-op success
     assert lib.kmsr_degrade_prepared(None, 0, 5, 64, 64, 0, 0, 64, None, None, None, 1, 13, 13, None, None, None,
                                      0, None, 8, 0, 0, 0, None, 0, None) == 0
+
+
+def test_folder_drivers_match_the_reference_chain(K, synth, bank, tmp_path, capsys):
+    """C_30.process_landsat_folder -> E.process_files and D.build_noise_pool on .npz patch files: file naming, per-file
+    skip semantics, RNG consumption and pixels equal to the reference functions applied file by file."""
+    import os
+    import random
+    from kmsr_b200 import patch_io as pio
+    kb, _ = bank
+    src, blur_dir, train_dir, goci = [str(tmp_path / d) for d in ("patches", "blurred", "train", "goci")]
+    for d in (src, goci):
+        os.makedirs(d)
+    hr = synth.make_hr(5, 3100, "textured")
+    rs = np.random.RandomState(9)
+    nav = {"latitude": rs.standard_normal((256, 256)).astype(np.float32), "longitude": rs.standard_normal((256, 256)).astype(np.float32)}
+    for i in range(5):
+        pio.write_groups(os.path.join(src, f"LC08_{i:02d}_denoised.npz"),
+                         {"denoised": {b: hr[i, c] for c, b in enumerate(pio.BAND_NAMES)}, "navigation_data": nav})
+    pio.write_groups(os.path.join(src, "LC08_97_denoised.npz"), {"geophysical_data": {"L_TOA_443": hr[0, 0]}})   # no 'denoised' group
+    pio.write_groups(os.path.join(src, "LC08_98_denoised.npz"),                                                 # wrong size for E
+                     {"denoised": {b: hr[0, c, :128, :128] for c, b in enumerate(pio.BAND_NAMES)}, "navigation_data": nav})
+    kpath = str(tmp_path / "kernel.npy")
+    np.save(kpath, kb[5])
+    K.C30.process_landsat_folder(src, kpath, blur_dir)
+    out = sorted(os.listdir(blur_dir))
+    assert out == [f"LC08_{i:02d}_denoised_blurred.npz" for i in range(5)] + ["LC08_98_denoised_blurred.npz"]
+    for i in range(5):
+        got = pio.read_group_bands(os.path.join(blur_dir, out[i]), "blurred")
+        ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kb[5]), 8).numpy()
+        check_pixels(got, ref, hr[i], name=out[i])
+        assert np.array_equal(pio.read_group_bands(os.path.join(blur_dir, out[i]), "denoised"), hr[i])
+    # E: listdir order binds the draws; the 128x128 file is rejected without a draw
+    pool = synth.make_noise_pool(32, 42)
+    ppath = str(tmp_path / "pool.npy")
+    np.save(ppath, pool)
+    ok, fail = K.E.process_files(blur_dir, ppath, train_dir, seed=42)
+    assert (ok, fail) == (5, 1)
+    order = [f for f in os.listdir(blur_dir) if f.endswith(".npz")]
+    np.random.seed(42)
+    for f in order:
+        if "_98_" in f:
+            continue
+        idx = np.random.randint(0, len(pool))
+        tr = os.path.join(train_dir, f.replace("_denoised_blurred.npz", "_train.npz"))
+        assert os.path.isfile(tr)
+        blurred = pio.read_group_bands(os.path.join(blur_dir, f), "blurred")
+        assert np.array_equal(pio.read_group_bands(tr, "lr"), blurred + pool[idx])          # E:74, bit exact
+        assert np.array_equal(pio.read_group_bands(tr, "hr"), pio.read_group_bands(os.path.join(blur_dir, f), "denoised"))
+        assert set(pio.read_navigation(tr)) == {"latitude", "longitude"}
+    # C_31: group 'hr' in, group 'lr' written into the same file
+    c31 = str(tmp_path / "c31")
+    os.makedirs(c31)
+    for i in range(2):
+        pio.write_groups(os.path.join(c31, f"p{i}.npz"), {"hr": {b: hr[i, c] for c, b in enumerate(pio.BAND_NAMES)}})
+    K.C31.process_landsat_folder(c31, kpath, str(tmp_path / "c31_out"), downscale_factor=4)
+    for i in range(2):
+        got = pio.read_group_bands(os.path.join(c31, f"p{i}.npz"), "lr")
+        ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kb[5]), 4).numpy()
+        assert got.shape == (5, 64, 64)
+        check_pixels(got, ref, hr[i], name=f"c31 p{i}")
+    # D: noise = geo - den, crops at CPython-random offsets in listdir order
+    geo = synth.make_hr(3, 3200, "textured", size=96)
+    den = geo - (rs.standard_normal(geo.shape) * 0.3).astype(np.float32)
+    for i in range(3):
+        pio.write_groups(os.path.join(goci, f"GK2_{i}.npz"), {"geophysical_data": {b: geo[i, c] for c, b in enumerate(pio.BAND_NAMES)},
+                                                             "denoised": {b: den[i, c] for c, b in enumerate(pio.BAND_NAMES)}})
+    pool2 = K.D.build_noise_pool(goci, str(tmp_path / "np" / "pool.npy"), str(tmp_path / "np" / "meta.npy"), samples_per_file=2,
+                                 patch_size=32, seed=42)
+    assert np.array_equal(np.load(str(tmp_path / "np" / "pool.npy")), pool2) and pool2.shape == (6, 5, 32, 32)
+    random.seed(42)
+    m = 0
+    for f in [f for f in os.listdir(goci) if f.endswith(".npz")]:
+        i = int(f.split("_")[1].split(".")[0])
+        noise = geo[i] - den[i]
+        for _ in range(2):
+            top = random.randint(0, 96 - 32)
+            left = random.randint(0, 96 - 32)
+            assert np.array_equal(pool2[m], noise[:, top:top + 32, left:left + 32])
+            m += 1
+    meta = np.load(str(tmp_path / "np" / "meta.npy"), allow_pickle=True)
+    assert len(meta) == 6 and meta[0]["patch_size"] == 32
+    capsys.readouterr()
+
+
+def test_create_patches_nc_writes_the_kept_windows(K, synth, tmp_path, capsys):
+    """CUT.create_patches_nc: (total, kept), file names in raster order, patch contents and cropped navigation."""
+    import os
+    from kmsr_b200 import patch_io as pio
+    scene = synth.make_scene(11, 640, 768, n_fill=2, n_cloud=2)
+    masked = orc.apply_water_mask(scene.copy(), 1e-6, 7.0)
+    nav = {"latitude": np.arange(640 * 768, dtype=np.float32).reshape(640, 768)}
+    total, kept = K.CUT.create_patches_nc(masked, 256, 0.5, 0.0, str(tmp_path / "cut"), "LC09", {"navigation_data": nav, "source_file": "s.nc"},
+                                          ext=".npz")
+    ref_keep = orc.keep_mask(masked, 256, 0.5, 0.0)
+    assert total == ref_keep.size and kept == int(ref_keep.sum())
+    names = sorted(os.listdir(str(tmp_path / "cut")))
+    want = [f"LC09_{i:03d}_{j:03d}.npz" for i in range(ref_keep.shape[0]) for j in range(ref_keep.shape[1]) if ref_keep[i, j]]
+    assert names == want
+    i, j = [int(t) for t in names[-1][5:12].split("_")]
+    p = pio.read_group_bands(str(tmp_path / "cut" / names[-1]), "geophysical_data")
+    assert np.array_equal(p, masked[:, i * 128:i * 128 + 256, j * 128:j * 128 + 256])
+    assert np.array_equal(pio.read_navigation(str(tmp_path / "cut" / names[-1]))["latitude"], nav["latitude"][i * 128:i * 128 + 256, j * 128:j * 128 + 256])
+    capsys.readouterr()

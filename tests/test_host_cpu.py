@@ -196,3 +196,33 @@ def test_world_size_2_gloo_sharding_and_stats_allreduce(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK" in outs[0]
+
+
+def test_patch_io_roundtrip_and_listing(tmp_path):
+    """The .npz group container of the folder drivers: groups, missing-group errors, append, listing order."""
+    from kmsr_b200 import patch_io as pio
+    rs = np.random.RandomState(1)
+    bands = {b: rs.standard_normal((8, 8)).astype(np.float32) for b in pio.BAND_NAMES}
+    nav = {"latitude": rs.standard_normal((8, 8)).astype(np.float32), "longitude": rs.standard_normal((8, 8)).astype(np.float32)}
+    p = str(tmp_path / "b_patch.npz")
+    pio.write_groups(p, {"denoised": bands, "navigation_data": nav}, {"source_file": "x"})
+    got = pio.read_group_bands(p, "denoised")
+    assert got.shape == (5, 8, 8) and all(np.array_equal(got[i], bands[b]) for i, b in enumerate(pio.BAND_NAMES))
+    assert set(pio.read_navigation(p)) == {"latitude", "longitude"}
+    with pytest.raises(ValueError):
+        pio.read_group_bands(p, "blurred")
+    q = str(tmp_path / "a_patch_blurred.npz")
+    pio.add_group(q, "blurred", got[:, ::2, ::2], src=p, history="h")
+    assert pio.read_group_bands(q, "blurred").shape == (5, 4, 4) and np.array_equal(pio.read_group_bands(q, "denoised"), got)
+    pio.write_training_sample(str(tmp_path / "c_train.npz"), got, got[:, ::2, ::2], nav)
+    assert np.array_equal(pio.read_group_bands(str(tmp_path / "c_train.npz"), "lr"), got[:, ::2, ::2])
+    (tmp_path / "notes.txt").write_text("x")
+    assert pio.list_patch_files(str(tmp_path), sort=True) == ["a_patch_blurred.npz", "b_patch.npz", "c_train.npz"]
+    assert sorted(pio.list_patch_files(str(tmp_path), sort=False)) == pio.list_patch_files(str(tmp_path), sort=True)
+    # a .nc file without the netCDF4 module fails loudly, per file
+    try:
+        import netCDF4  # noqa: F401
+    except Exception:
+        (tmp_path / "z.nc").write_bytes(b"CDF")
+        with pytest.raises(ImportError):
+            pio.read_group_bands(str(tmp_path / "z.nc"), "denoised")
