@@ -19,6 +19,7 @@
 //    distinct rows a warp reads at once never collide); pixels are pivot-shifted and multiplied as
 //    packed FFMA2 pairs exactly like the headline kernel.
 #include <stdlib.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tma_util.cuh"
@@ -31,6 +32,7 @@ constexpr int kConsumers = 8;                  // consumer warps per CTA
 constexpr int kProducers = 4;                  // producer warps (one elected thread each)
 constexpr int kThreadsS = (kConsumers + kProducers) * 32;
 constexpr int kTX = 4;                         // LR columns per lane
+constexpr int kRenameQ = 5;                    // accumulator sets are renamed (steps unrolled by Q) up to this many
 
 template <int K, int S>
 struct Cfg {
@@ -73,6 +75,7 @@ struct StreamArgs {
     int nchunks;            // H / S
     int pad_mode, noise_mode;
     unsigned ringOff, barOff, wOff;
+    int wbuf;               // weight buffers per warp: 2 = the next band's kernel is prefetched, 1 = staged between bands
 };
 
 template <int K, int S>
@@ -145,46 +148,66 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
     const int g = lane_on ? g_raw : a.ng - 1;
     const unsigned char* sring = smem_raw + a.ringOff + (size_t)s * D * a.slotBytes;
     const uint32_t sfull = full0 + 8 * s * D, sempty = empty0 + 8 * s * D;
-    float* wsm = reinterpret_cast<float*>(smem_raw + a.wOff) + (size_t)warp * G::WROWS * G::WP;
+    // per-warp weight copies: buffer 0, and buffer 1 when the next band's kernel is prefetched (a.wbuf == 2)
+    float* wbase = reinterpret_cast<float*>(smem_raw + a.wOff) + (size_t)warp * a.wbuf * (G::WROWS * G::WP);
     const bool replicate = a.pad_mode == KMSR_PAD_REPLICATE;
     const bool noisy = a.noise_mode != KMSR_NOISE_NONE;
     const long long ohw = (long long)a.Ho * a.Wo;
     const int nsteps = a.Ho + G::Q - 1;
 
-    // ring bookkeeping: chunks of this stream are numbered continuously across its items
-    int wslot = 0, rslot = 0;          // next slot to wait for / to release
+    // ring bookkeeping, per item: chunks [rel, wai) of the item are resident, chunk `rel` sits in slot rslot
+    int wslot = 0, rslot = 0;
     uint32_t wpar = 0;
-    long long waited = 0, released = 0;   // chunk counters (global within the stream)
 
-    for (int r = lane; r < G::WROWS * G::WP; r += 32) wsm[r] = 0.0f;       // rows >= KW and pitch padding stay zero
+    for (int r = lane; r < a.wbuf * G::WROWS * G::WP; r += 32) wbase[r] = 0.0f;    // rows >= KW and pitch padding stay zero
     __syncwarp();
 
-    long long base = 0;                // chunk counter of the current item's first chunk
-    for (long long item = (long long)blockIdx.x * a.ns + s; item < a.nitems; item += GS, base += a.nchunks) {
-        const long long band = item / a.nblk;
-        const int blk = (int)(item - band * a.nblk);
-        const long long n = band / a.C;
-        const int c = (int)(band - n * a.C);
-        const int kid = a.kidx ? __ldg(a.kidx + n) : 0;
-        const bool edge_l = replicate && blk == 0, edge_r = replicate && blk == a.nblk - 1;
+    // composite kernel of (kid, c) -> weight buffer `buf` with cp.async (4-byte copies: the bank rows are not 16-byte
+    // multiples for every K); the caller commits and waits
+    auto stage_weights = [&](int buf, int kid, int c) {
+        const float* kc = a.comp + ((long long)kid * a.C + c) * (G::KW * a.compPitch);
+        const uint32_t dst = smem_u32(wbase + (size_t)buf * (G::WROWS * G::WP));
+        for (int e = lane; e < G::KW * G::KW; e += 32) {
+            const int u = e / G::KW, v = e - u * G::KW;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * (u * G::WP + v)), "l"(kc + u * a.compPitch + v)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    struct ItemParams { long long band; int blk, c, kid, nid; float ds, scale; };
+    auto load_params = [&](long long item) {
+        ItemParams q;
+        q.band = item / a.nblk;
+        q.blk = (int)(item - q.band * a.nblk);
+        const long long n = q.band / a.C;
+        q.c = (int)(q.band - n * a.C);
+        q.kid = a.kidx ? __ldg(a.kidx + n) : 0;
+        q.nid = noisy ? __ldg(a.nidx + n) : 0;
+        q.ds = __ldg(a.dsum + (long long)q.kid * a.C + q.c);
+        q.scale = a.noise_mode == KMSR_NOISE_SIGMA ? __ldg(a.sigma + (long long)q.kid * a.C + q.c) : 1.0f;
+        return q;
+    };
 
-        // composite kernel of this band -> the warp's weight copy (pitch WP, rows >= KW zero)
-        {
-            const float* kc = a.comp + ((long long)kid * a.C + c) * (G::KW * a.compPitch);
-            __syncwarp();
-            for (int e = lane; e < G::KW * G::KW; e += 32) {
-                const int u = e / G::KW, v = e - u * G::KW;
-                wsm[u * G::WP + v] = __ldg(kc + u * a.compPitch + v);
-            }
-            __syncwarp();
+    long long item = (long long)blockIdx.x * a.ns + s;
+    ItemParams cur;
+    int wcur = 0;
+    if (item < a.nitems) {
+        cur = load_params(item);
+        stage_weights(0, cur.kid, cur.c);
+    }
+    for (; item < a.nitems; item += GS) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        const float* wsm = wbase + (size_t)wcur * (G::WROWS * G::WP);
+        const ItemParams it = cur;
+        const bool has_next = item + GS < a.nitems;
+        if (has_next) {
+            cur = load_params(item + GS);                      // consumed at the next band: the latency hides behind this one
+            if (a.wbuf == 2) { stage_weights(wcur ^ 1, cur.kid, cur.c); }
         }
-        const float ds = __ldg(a.dsum + (long long)kid * a.C + c);
-        float scale = 1.0f;
-        const float* nz = nullptr;
-        if (noisy) {
-            nz = a.pool + ((long long)__ldg(a.nidx + n) * a.C + c) * ohw;
-            if (a.noise_mode == KMSR_NOISE_SIGMA) scale = __ldg(a.sigma + (long long)kid * a.C + c);
-        }
+        const bool edge_l = replicate && it.blk == 0, edge_r = replicate && it.blk == a.nblk - 1;
+        const float ds = it.ds, scale = it.scale;
+        const float* nz = a.pool + ((long long)it.nid * a.C + it.c) * ohw;
 
         u64 A[G::Q][kTX];
 #pragma unroll
@@ -193,32 +216,36 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
             for (int x = 0; x < kTX; ++x) A[q][x] = 0ull;
         float pv = 0.0f;
         u64 npv2 = 0ull;
+        int rel = 0, wai = 0;                                  // chunks of this item released / waited for
 
         // output columns after the reduce-scatter over the S row lanes
-        const int col0 = blk * (a.BW / S) + kTX * g;          // first LR column of this lane group
+        const int col0 = it.blk * (a.BW / S) + kTX * g;       // first LR column of this lane group
         const int ox = S == 8 ? (ly >> 1) : (S == 4 ? ly : 2 * ly);
         const bool writer = lane_on && (S != 8 || (ly & 1) == 0);
+        float* outp = a.lr + it.band * ohw + col0 + ox;
+        const float* nzp = nz + col0 + ox;
+        const int lane_off = G::GW * g;
 
-#pragma unroll 1
-        for (int i = 0; i < nsteps; ++i) {
+        // One step.  SH = i mod Q when the accumulator sets are renamed (Q <= kRenameQ: set j holds output rows
+        // Y == j mod Q), SH = -1 when they are rotated by value (set q holds output row i - q).
+        auto step = [&](auto sh_tag, const int i) {
+            constexpr int SH = decltype(sh_tag)::value;
             // ---- rows this step needs: padded rows S*i .. S*i+S-1 = image rows S*i - PAD + ly ----
             const int rr_raw = S * i + ly - G::PAD;
             const int rr = min(max(rr_raw, 0), a.H - 1);
             const bool row_ok = rr_raw >= 0 && rr_raw < a.H;               // zero padding: rows outside are zeros
             const int hi_chunk = min(max(S * i + S - 1 - G::PAD, 0), a.H - 1) / S;
-            while (waited <= base + hi_chunk) {
+            while (wai <= hi_chunk) {
                 mbar_wait(sfull + 8 * wslot, wpar);
                 if (++wslot == D) { wslot = 0; wpar ^= 1; }
-                ++waited;
+                ++wai;
             }
-            const long long ck = base + rr / S;                             // chunk of this lane's row
-            const int slot = (int)(ck % D);
-            const float* src = reinterpret_cast<const float*>(sring + (size_t)slot * a.slotBytes) +
-                               (rr % S) * a.pitchF + G::GW * g;
+            int slot = rslot + (rr / S - rel);                              // chunk rel sits in slot rslot
+            if (slot >= D) slot -= D;
+            const float* src = reinterpret_cast<const float*>(sring + (size_t)slot * a.slotBytes) + (rr % S) * a.pitchF + lane_off;
             if (i == 0) {
-                // pivot: pixel (0, first column of the lane group) -- row 0 is in the item's first chunk
-                const int s0 = (int)(base % D);
-                pv = reinterpret_cast<const float*>(sring + (size_t)s0 * a.slotBytes)[G::AL + G::GW * g];
+                // pivot: pixel (0, first column of the lane group) -- row 0 is in the item's first chunk (slot rslot)
+                pv = reinterpret_cast<const float*>(sring + (size_t)rslot * a.slotBytes)[G::AL + lane_off];
                 if (!isfinite(pv)) pv = 0.0f;
                 npv2 = pack2(-pv, -pv);
             }
@@ -230,22 +257,20 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
             }
             // release the chunks no later step needs (all of them after the item's last step)
             {
-                const long long lo_next = i + 1 < nsteps ? base + min(max(S * (i + 1) - G::PAD, 0), a.H - 1) / S
-                                                          : base + a.nchunks;
+                const int lo_next = i + 1 < nsteps ? min(max(S * (i + 1) - G::PAD, 0), a.H - 1) / S : a.nchunks;
                 __syncwarp();
-                while (released < lo_next) {
+                while (rel < lo_next) {
                     if (lane == 0) mbar_arrive(sempty + 8 * rslot);
                     if (++rslot == D) rslot = 0;
-                    ++released;
+                    ++rel;
                 }
             }
             // noise of the row that completes in this step: issue the load before the arithmetic
             const int Y = i - (G::Q - 1);
             float nzv[2] = {0.0f, 0.0f};
             if (noisy && writer && Y >= 0) {
-                const float* np_ = nz + (long long)Y * a.Wo + col0 + ox;
-                nzv[0] = __ldg(np_);
-                if (S == 2) nzv[1] = __ldg(np_ + 1);
+                nzv[0] = __ldg(nzp + (long long)Y * a.Wo);
+                if (S == 2) nzv[1] = __ldg(nzp + (long long)Y * a.Wo + 1);
             }
 
             // d[j] = pixel column GW*g - PAD + j of the block, j < SEG
@@ -287,11 +312,13 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
             // ---- multiply-accumulate: composite row u = ly + S*q meets output row i - q ----
 #pragma unroll
             for (int q = 0; q < G::Q; ++q) {
+                constexpr int dummy = 0; (void)dummy;
+                const int j = SH < 0 ? q : (SH - q + G::Q) % G::Q;          // accumulator set of output row i - q
                 const int u = ly + S * q;
                 const float* wrow = wsm + u * G::WP;
                 u64 T[kTX];
 #pragma unroll
-                for (int x = 0; x < kTX; ++x) T[x] = A[q][x];
+                for (int x = 0; x < kTX; ++x) T[x] = A[j][x];
 #pragma unroll
                 for (int t4 = 0; t4 < (G::TP + 1) / 2; ++t4) {
                     const ulonglong2 w2 = reinterpret_cast<const ulonglong2*>(wrow)[t4];
@@ -305,14 +332,15 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
                 // output the reference keeps
                 const bool live = (q + 1) * S <= G::KW || u < G::KW;
 #pragma unroll
-                for (int x = 0; x < kTX; ++x) if (live) A[q][x] = T[x];
+                for (int x = 0; x < kTX; ++x) if (live) A[j][x] = T[x];
             }
 
             // ---- the oldest set completes: reduce over the S row lanes, epilogue, store ----
+            constexpr int JO = SH < 0 ? G::Q - 1 : (SH + 1) % G::Q;         // == (SH - (Q-1)) mod Q
             if (Y >= 0) {
                 float v[kTX];
 #pragma unroll
-                for (int x = 0; x < kTX; ++x) v[x] = lo2(A[G::Q - 1][x]) + hi2(A[G::Q - 1][x]);
+                for (int x = 0; x < kTX; ++x) v[x] = lo2(A[JO][x]) + hi2(A[JO][x]);
                 float r0, r1 = 0.0f;
                 {
                     const bool up = (ly & (S / 2)) != 0;
@@ -331,7 +359,7 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
                 }
                 if (S == 8) r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
                 if (writer) {
-                    float* out = a.lr + band * ohw + (long long)Y * a.Wo + col0 + ox;
+                    float* out = outp + (long long)Y * a.Wo;
                     float res = pv + fmaf(pv, ds, r0);
                     if (noisy) res = fmaf(scale, nzv[0], res);
                     out[0] = res;
@@ -342,13 +370,38 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
                     }
                 }
             }
-            // rotate the accumulator sets by value: set q becomes set q + 1, set 0 starts empty
+            if (SH < 0) {
+                // rotate the accumulator sets by value: set q becomes set q + 1, set 0 starts empty
 #pragma unroll
-            for (int q = G::Q - 1; q > 0; --q)
+                for (int q = G::Q - 1; q > 0; --q)
 #pragma unroll
-                for (int x = 0; x < kTX; ++x) A[q][x] = A[q - 1][x];
+                    for (int x = 0; x < kTX; ++x) A[q][x] = A[q - 1][x];
 #pragma unroll
-            for (int x = 0; x < kTX; ++x) A[0][x] = 0ull;
+                for (int x = 0; x < kTX; ++x) A[0][x] = 0ull;
+            } else {
+#pragma unroll
+                for (int x = 0; x < kTX; ++x) A[JO][x] = 0ull;             // becomes the fresh set of step i + 1
+            }
+        };
+
+        if constexpr (G::Q <= kRenameQ) {
+#pragma unroll 1
+            for (int i = 0; i < nsteps; i += G::Q) {
+                step(std::integral_constant<int, 0>{}, i);
+                if constexpr (G::Q > 1) { if (i + 1 < nsteps) step(std::integral_constant<int, 1 % G::Q>{}, i + 1); }
+                if constexpr (G::Q > 2) { if (i + 2 < nsteps) step(std::integral_constant<int, 2 % G::Q>{}, i + 2); }
+                if constexpr (G::Q > 3) { if (i + 3 < nsteps) step(std::integral_constant<int, 3 % G::Q>{}, i + 3); }
+                if constexpr (G::Q > 4) { if (i + 4 < nsteps) step(std::integral_constant<int, 4 % G::Q>{}, i + 4); }
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < nsteps; ++i) step(std::integral_constant<int, -1>{}, i);
+        }
+        if (a.wbuf == 2) {
+            wcur ^= 1;
+        } else if (has_next) {
+            __syncwarp();                                      // every lane is done reading the single buffer
+            stage_weights(0, cur.kid, cur.c);
         }
     }
 }
@@ -366,10 +419,16 @@ int launch_kS(const CUtensorMap& tmap, StreamArgs& t, int sms, cudaStream_t st) 
     t.slotBytes = (t.chunkBytes + 127) / 128 * 128;
     t.nchunks = t.H / S;
     t.ng = t.BW / G::GW;
-    const size_t wbytes = (size_t)kConsumers * G::WROWS * G::WP * 4;
     int dev = 0, max_smem = 0;
     KMSR_CUDA_OK(cudaGetDevice(&dev));
     KMSR_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    // two weight buffers per warp (prefetch of the next band's kernel) when the ring keeps at least 4 slots
+    t.wbuf = 2;
+    size_t wbytes = (size_t)kConsumers * 2 * G::WROWS * G::WP * 4;
+    if (((size_t)max_smem - (wbytes + 2 * 8 * 8 * 16 + 1024)) / ((size_t)t.ns * t.slotBytes) < 4) {
+        t.wbuf = 1;
+        wbytes /= 2;
+    }
     const size_t fixed = wbytes + 2 * 8 * 8 * 16 + 1024;
     int depth = (int)(((size_t)max_smem - fixed) / ((size_t)t.ns * t.slotBytes));
     // a ring must at least hold the rows one step touches plus one tile in flight
