@@ -6,8 +6,8 @@ namespace kmsr {
 
 // data[c,i] == invalid -> NaN in place (CUT:102); masked = NaN where NIR not in [tmin,tmax] (CUT:108-113)
 __global__ void __launch_bounds__(256)
-water_mask_kernel(float* __restrict__ data, int C, long long hw, int nir, float invalid, float tmin,
-                  float tmax, float* __restrict__ masked) {
+water_mask_kernel(float* __restrict__ data, int C, long long hw, int nir, float invalid, float tmin, float tmax,
+                  float* __restrict__ masked) {
     const float qnan = __int_as_float(0x7fc00000);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw;
          i += (long long)gridDim.x * blockDim.x) {
@@ -23,6 +23,42 @@ water_mask_kernel(float* __restrict__ data, int C, long long hw, int nir, float 
     }
 }
 
+// 128-bit form (hw % 4 == 0, 16-byte aligned bases, C <= 8): all band loads of a pixel quad are in flight
+// together; the in-place write-back happens only where a fill value was actually replaced.
+template <int C>
+__global__ void __launch_bounds__(256)
+water_mask_vec_kernel(float4* __restrict__ data, long long hw4, int nir, float invalid, float tmin,
+                      float tmax, float4* __restrict__ masked) {
+    const float qnan = __int_as_float(0x7fc00000);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hw4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 d[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) d[c] = data[(long long)c * hw4 + i];
+        float4 n = d[0];
+#pragma unroll
+        for (int c = 1; c < C; ++c)
+            if (c == nir) n = d[c];
+        const bool w0 = (n.x != invalid) && (n.x >= tmin) && (n.x <= tmax);
+        const bool w1 = (n.y != invalid) && (n.y >= tmin) && (n.y <= tmax);
+        const bool w2 = (n.z != invalid) && (n.z >= tmin) && (n.z <= tmax);
+        const bool w3 = (n.w != invalid) && (n.w >= tmin) && (n.w <= tmax);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            {
+                float4 v = d[c];
+                const bool ch = v.x == invalid || v.y == invalid || v.z == invalid || v.w == invalid;
+                if (v.x == invalid) v.x = qnan;
+                if (v.y == invalid) v.y = qnan;
+                if (v.z == invalid) v.z = qnan;
+                if (v.w == invalid) v.w = qnan;
+                if (ch) data[(long long)c * hw4 + i] = v;
+                masked[(long long)c * hw4 + i] = make_float4(w0 ? v.x : qnan, w1 ? v.y : qnan, w2 ? v.z : qnan, w3 ? v.w : qnan);
+            }
+        }
+    }
+}
+
 // stage 1: NaN count of every stride x stride cell over all bands -> cells [ch, cw] int32
 __global__ void __launch_bounds__(256)
 nan_cells_kernel(const float* __restrict__ masked, int C, int H, int W, int cell, int ch, int cw,
@@ -32,11 +68,43 @@ nan_cells_kernel(const float* __restrict__ masked, int C, int H, int W, int cell
     const int y0 = ci * cell, x0 = cj * cell;
     const int hh = min(cell, H - y0), ww = min(cell, W - x0);
     int cnt = 0;
-    for (int c = 0; c < C; ++c) {
-        const float* base = masked + ((long long)c * H + y0) * W + x0;
-        for (int i = threadIdx.x; i < hh * ww; i += blockDim.x) {
-            const float v = base[(long long)(i / ww) * W + (i % ww)];
-            cnt += (v != v);
+    if ((W & 3) == 0 && (x0 & 3) == 0 && (ww & 3) == 0 && (((uintptr_t)masked) & 15) == 0) {
+        // rows of the cell as float4: a warp covers 128 columns per load, four row loads in flight per thread
+        const int w4 = ww >> 2, rows = C * hh, per_it = 256 / min(w4, 256);
+        const int lx = threadIdx.x % w4, lr = threadIdx.x / w4;
+        if (w4 <= 256 && lr < per_it) {
+            for (int r0 = lr; r0 < rows; r0 += 4 * per_it) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + u * per_it;
+                    if (r < rows) {
+                        const int c = r / hh, y = r - c * hh;
+                        v[u] = *reinterpret_cast<const float4*>(masked + ((long long)c * H + y0 + y) * W + x0 + 4 * lx);
+                    } else {
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    cnt += (v[u].x != v[u].x) + (v[u].y != v[u].y) + (v[u].z != v[u].z) + (v[u].w != v[u].w);
+            }
+        } else if (w4 > 256) {
+            for (int r = 0; r < rows; ++r) {
+                const int c = r / hh, y = r - c * hh;
+                for (int x = threadIdx.x; x < w4; x += 256) {
+                    const float4 t = *reinterpret_cast<const float4*>(masked + ((long long)c * H + y0 + y) * W + x0 + 4 * x);
+                    cnt += (t.x != t.x) + (t.y != t.y) + (t.z != t.z) + (t.w != t.w);
+                }
+            }
+        }
+    } else {
+        for (int c = 0; c < C; ++c) {
+            const float* base = masked + ((long long)c * H + y0) * W + x0;
+            for (int i = threadIdx.x; i < hh * ww; i += blockDim.x) {
+                const float v = base[(long long)(i / ww) * W + (i % ww)];
+                cnt += (v != v);
+            }
         }
     }
 #pragma unroll
@@ -93,6 +161,23 @@ keep_direct_kernel(const float* __restrict__ masked, int C, int H, int W, int P,
 int launch_water_mask(float* data, int C, long long hw, int nir, float invalid, float tmin, float tmax,
                       float* masked, cudaStream_t st) {
     if (hw == 0) return KMSR_OK;
+    if ((hw & 3) == 0 && C <= 6 && (((uintptr_t)data | (uintptr_t)masked) & 15) == 0) {
+        long long blocks = (hw / 4 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        float4* d4 = (float4*)data;
+        float4* m4 = (float4*)masked;
+        const unsigned gb = (unsigned)blocks;
+        switch (C) {
+            case 1: water_mask_vec_kernel<1><<<gb, 256, 0, st>>>(d4, hw / 4, nir, invalid, tmin, tmax, m4); break;
+            case 2: water_mask_vec_kernel<2><<<gb, 256, 0, st>>>(d4, hw / 4, nir, invalid, tmin, tmax, m4); break;
+            case 3: water_mask_vec_kernel<3><<<gb, 256, 0, st>>>(d4, hw / 4, nir, invalid, tmin, tmax, m4); break;
+            case 4: water_mask_vec_kernel<4><<<gb, 256, 0, st>>>(d4, hw / 4, nir, invalid, tmin, tmax, m4); break;
+            case 5: water_mask_vec_kernel<5><<<gb, 256, 0, st>>>(d4, hw / 4, nir, invalid, tmin, tmax, m4); break;
+            default: water_mask_vec_kernel<6><<<gb, 256, 0, st>>>(d4, hw / 4, nir, invalid, tmin, tmax, m4); break;
+        }
+        KMSR_LAUNCH_CHECK("water_mask_vec_kernel");
+        return KMSR_OK;
+    }
     long long blocks = (hw + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     water_mask_kernel<<<(unsigned)blocks, 256, 0, st>>>(data, C, hw, nir, invalid, tmin, tmax, masked);

@@ -46,6 +46,7 @@ band_stats_kernel(const float* __restrict__ x, int C, long long hw, long long st
     unsigned cnt = 0;
     if (vec) {
         const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll 4
         for (long long i = threadIdx.x; i < (hw >> 2); i += blockDim.x) {
             const float4 v = p4[i];
             if (v.x == v.x) { s += v.x - pv; ++cnt; }
@@ -68,6 +69,7 @@ band_stats_kernel(const float* __restrict__ x, int C, long long hw, long long st
     float q = 0.0f;
     if (vec) {
         const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll 4
         for (long long i = threadIdx.x; i < (hw >> 2); i += blockDim.x) {
             const float4 v = p4[i];
             float d;
