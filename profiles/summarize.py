@@ -50,10 +50,11 @@ def num(v):
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r13"
-    rep = os.path.join(OUT, f"{tag}_tma.ncu-rep")
+    which = sys.argv[2] if len(sys.argv) > 2 else "tma"          # "tma" (bench.py capture) or "stream" (tools/stream_case.py)
+    rep = os.path.join(OUT, f"{tag}_{which}.ncu-rep")
     rows = ncu_csv(rep, "raw")
     hdr, units, vals = rows[0], rows[1], rows[2]
-    rec = {"source": f"gpurun_out/{tag}_tma.ncu-rep (ncu --set full --clock-control none --import-source on, 1 launch)",
+    rec = {"source": f"gpurun_out/{tag}_{which}.ncu-rep (ncu --set full --clock-control none --import-source on, 1 launch)",
            "kernel": vals[hdr.index("Kernel Name")], "metrics": {}}
     for k in KEYS:
         if k in hdr:
@@ -70,20 +71,26 @@ def main():
     wr = m["dram__bytes_write.sum"]["value"] * scale[m["dram__bytes_write.sum"]["unit"]]
     rec["dram_bytes_per_launch"] = rd + wr
     bench = os.path.join(OUT, f"{tag}_bench.json")
-    if os.path.isfile(bench):
+    sfx = "" if which == "tma" else f"_{which}"
+    if which != "tma":
+        plain = os.path.join(OUT, f"{tag}_plain3.log")
+        if os.path.isfile(plain):
+            rec["plain_run"] = open(plain).read().strip().splitlines()[-1]
+    if which == "tma" and os.path.isfile(bench):
         line = [l for l in open(bench).read().splitlines() if l.startswith("{")][-1]
         b = json.loads(line)
         rec["bench_line"] = {k: b[k] for k in ("value", "unit", "ms_per_step", "roofline", "clocks", "gpu_launches")}
         algo_bytes = b["roofline"]["bytes_per_pair"] * b["config"]["patches_per_gpu"]
         rec["algorithmic_bytes_per_launch"] = algo_bytes
         rec["traffic_over_algorithmic"] = rec["dram_bytes_per_launch"] / algo_bytes
-    json.dump(rec, open(os.path.join(ROOT, "profiles", f"{ROUND}_{tag}_kernel.json"), "w"), indent=1)
-    json.dump({"dram_bytes_per_launch": rec["dram_bytes_per_launch"], "kernel": "degrade_tma_kernel<0>",
-               "source": f"profiles/{ROUND}_{tag}_kernel.json"}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    json.dump(rec, open(os.path.join(ROOT, "profiles", f"{ROUND}_{tag}{sfx}_kernel.json"), "w"), indent=1)
+    if which == "tma":
+        json.dump({"dram_bytes_per_launch": rec["dram_bytes_per_launch"], "kernel": "degrade_tma_kernel<0, false>",
+                   "source": f"profiles/{ROUND}_{tag}_kernel.json"}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 
     # launch list
     src = os.path.join(OUT, f"{tag}_launches.csv")
-    if os.path.isfile(src):
+    if which == "tma" and os.path.isfile(src):
         lines = [l for l in open(src) if l.startswith('"')]
         open(os.path.join(ROOT, "profiles", f"{ROUND}_{tag}_launches.csv"), "w").writelines(lines)
         rd_ = list(csv.DictReader(io.StringIO("".join(lines))))
@@ -112,7 +119,7 @@ def main():
     tot_s = sum(int(r[ix["# Samples"]]) for r in data)
     agg = {s: sum(int(r[ix[s]]) for r in data) for s in stalls}
     base = int(data[0][0], 16)
-    with open(os.path.join(ROOT, "profiles", f"{ROUND}_{tag}_stalls.txt"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", f"{ROUND}_{tag}{sfx}_stalls.txt"), "w") as f:
         f.write(f"# warp-stall samples of {rec['kernel']} ({tag}); {tot_s} samples, {len(data)} SASS instructions\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
             if v:

@@ -520,3 +520,17 @@ def test_create_patches_nc_writes_the_kept_windows(K, synth, tmp_path, capsys):
     assert np.array_equal(p, masked[:, i * 128:i * 128 + 256, j * 128:j * 128 + 256])
     assert np.array_equal(pio.read_navigation(str(tmp_path / "cut" / names[-1]))["latitude"], nav["latitude"][i * 128:i * 128 + 256, j * 128:j * 128 + 256])
     capsys.readouterr()
+
+
+def test_per_patch_dynamic_kernels(K, synth):
+    """a bank with one kernel per patch ([N,5,13,13], kidx = arange(N)) -- the output format of
+    muti_kernel/train.py:118-187 -- goes through the same entry point."""
+    n = 24
+    hr = synth.make_hr(n, 3300, "textured")
+    kb = synth.softmax_kernels(13, 99, n=n)                      # [N, 5, 13, 13]
+    lr = K.ops.degrade_batch(torch.from_numpy(hr).cuda(), torch.from_numpy(kb).cuda(), kidx=np.arange(n, dtype=np.int32),
+                             factor=8).cpu().numpy()
+    assert K.lib.last_algo() == "tma"
+    for i in range(0, n, 5):
+        ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kb[i]), 8).numpy()
+        check_pixels(lr[i], ref, hr[i], name=f"dynamic kernel {i}")
