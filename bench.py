@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--patches", type=int, default=4096, help="patches per GPU per step")
-    ap.add_argument("--algo", default="auto", choices=["auto", "tiled", "tma"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "tiled", "tma", "stream"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
