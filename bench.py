@@ -255,9 +255,10 @@ def main():
     # ---- end to end from host buffers ("e2e") --------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        hr_host = torch.empty((n, C, P, P), dtype=torch.float32).pin_memory()
-        hr_host.copy_(hr)
-        lr_host = torch.empty((n, C, LR, LR), dtype=torch.float32).pin_memory()
+        with shard.numa_local(local):            # staging buffers on the GPU's own NUMA node (matters at N > 1)
+            hr_host = torch.empty((n, C, P, P), dtype=torch.float32).pin_memory()
+            hr_host.copy_(hr)
+            lr_host = torch.empty((n, C, LR, LR), dtype=torch.float32).pin_memory()
         e_steps = max(3, min(args.steps, 5))
         for _ in range(2):
             syn.run_host(hr_host, kidx, nidx, lr_host)

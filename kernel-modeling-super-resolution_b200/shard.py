@@ -60,6 +60,53 @@ def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
     return rank, local, world
 
 
+class numa_local:
+    """Context manager: run the enclosed host code on the CPUs that are local to GPU `device` (sysfs
+    `local_cpulist` of its PCI function), so that pinned staging buffers allocated inside land on the GPU's own
+    NUMA node -- with 8 ranks pushing ~55 GB/s each, remote-socket staging memory halves the end-to-end rate.
+    No-op when the topology cannot be read."""
+
+    def __init__(self, device: int):
+        self.device = device
+        self.saved = None
+
+    @staticmethod
+    def _cpus(device: int):
+        try:
+            p = torch.cuda.get_device_properties(device)
+            path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/local_cpulist"
+            cpus = set()
+            for part in open(path).read().strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+            return cpus
+        except Exception:
+            return set()
+
+    def __enter__(self):
+        cpus = self._cpus(self.device)
+        try:
+            allowed = os.sched_getaffinity(0)
+            cpus &= allowed
+            if cpus and cpus != allowed:
+                self.saved = allowed
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
 def local_stat_sums(mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
     """[N,C] per-patch means / stds of this rank -> f64 [2C+1] = (sum mean, sum std, N)."""
     c = mean.shape[1]
