@@ -534,3 +534,68 @@ def test_per_patch_dynamic_kernels(K, synth):
     for i in range(0, n, 5):
         ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kb[i]), 8).numpy()
         check_pixels(lr[i], ref, hr[i], name=f"dynamic kernel {i}")
+
+
+def test_new_entry_points_reject_bad_arguments(K, synth, bank):
+    """kmsr_degrade_windows / kmsr_degrade_stats_prepared / KMSR_ALGO_STREAM: argument errors come back as codes."""
+    import ctypes as C
+    lib = K.lib.lib()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    kb, _ = bank
+    pb = K.ops.prepare_kernels(torch.from_numpy(kb[0]).cuda(), 8)
+    scene = torch.zeros(5, 512, 512, device="cuda")
+    offs = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out = torch.zeros(1, 5, 32, 32, device="cuda")
+    # window larger than the scene
+    rc = lib.kmsr_degrade_windows(vp(scene), 5, 128, 512, 128 * 512, 512, vp(offs), 1, 256, 256, 128, vp(pb.comp), vp(pb.dsum),
+                                  1, 13, 13, None, None, None, 0, None, 8, 0, 0, 0, vp(out), 0, None)
+    assert rc == K.lib.E_INVALID and "does not fit" in K.lib.last_error()
+    # the TMA kernel needs the caller's alignment promise; without it AUTO falls back to the tiled kernel
+    rc = lib.kmsr_degrade_windows(vp(scene), 5, 512, 512, 512 * 512, 512, vp(offs), 1, 256, 256, 1, vp(pb.comp), vp(pb.dsum),
+                                  1, 13, 13, None, None, None, 0, None, 8, 0, 0, 0, vp(out), K.lib.ALGO_TMA, None)
+    assert rc == K.lib.E_UNSUPPORTED and "multiples of 4" in K.lib.last_error()
+    rc = lib.kmsr_degrade_windows(vp(scene), 5, 512, 512, 512 * 512, 512, vp(offs), 1, 256, 256, 1, vp(pb.comp), vp(pb.dsum),
+                                  1, 13, 13, None, None, None, 0, None, 8, 0, 0, 0, vp(out), 0, None)
+    assert rc == 0 and K.lib.last_algo() == "tiled"
+    # statistics entry point: missing outputs / short workspace
+    hr = torch.zeros(2, 5, 256, 256, device="cuda")
+    lr = torch.zeros(2, 5, 32, 32, device="cuda")
+    m = torch.zeros(2, 5, dtype=torch.float64, device="cuda")
+    ws = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    rc = lib.kmsr_degrade_stats_prepared(vp(hr), 2, 5, 256, 256, 5 * 65536, vp(pb.comp), vp(pb.dsum), 1, 13, 13, None, None, None, 0,
+                                         None, 8, 0, 0, 0, vp(lr), None, vp(m), None, vp(ws), 16, 0, None)
+    assert rc == K.lib.E_INVALID
+    rc = lib.kmsr_degrade_stats_prepared(vp(hr), 2, 5, 256, 256, 5 * 65536, vp(pb.comp), vp(pb.dsum), 1, 13, 13, None, None, None, 0,
+                                         None, 8, 0, 0, 0, vp(lr), vp(m), vp(m), None, vp(ws), 16, 0, None)
+    assert rc == K.lib.E_INVALID and "workspace" in K.lib.last_error()
+    # the streaming kernel refuses what it does not cover (even kernel, decimation)
+    with pytest.raises(K.lib.KmsrError):
+        K.ops.degrade_batch(hr, torch.rand(5, 12, 12, device="cuda"), factor=8, algo="stream")
+    with pytest.raises(K.lib.KmsrError):
+        K.ops.degrade_batch(hr, torch.from_numpy(kb[0]).cuda(), factor=4, down_mode="decimate", pad_mode="zero", algo="stream")
+    # ... and AUTO still serves them (tiled)
+    K.ops.degrade_batch(hr, torch.rand(5, 12, 12, device="cuda"), factor=8)
+    assert K.lib.last_algo() == "tiled"
+
+
+def test_shapes_the_streaming_kernels_hand_to_each_other(K, synth, bank):
+    """AUTO routing: headline shape -> tma, sweep shapes -> stream, odd sizes -> tiled; all three agree."""
+    kb, _ = bank
+    hr = torch.from_numpy(synth.make_hr(4, 3400, "textured")).cuda()
+    kd = torch.from_numpy(kb[7]).cuda()
+    a = K.ops.degrade_batch(hr, kd, factor=8)
+    assert K.lib.last_algo() == "tma"
+    b = K.ops.degrade_batch(hr, kd, factor=8, algo="stream")
+    c = K.ops.degrade_batch(hr, kd, factor=8, algo="tiled")
+    rngs = (hr.amax(dim=(2, 3)) - hr.amin(dim=(2, 3)))[:, :, None, None]
+    assert float(((a - b).abs() / rngs).max()) <= 2e-6 and float(((a - c).abs() / rngs).max()) <= 5e-6
+    K.ops.degrade_batch(hr[:, :, :250, :250].contiguous(), kd, factor=8)          # 250 is not a multiple of 8
+    assert K.lib.last_algo() == "tiled"
+    K.ops.degrade_batch(hr[:, :, :128, :128].contiguous(), kd, factor=4)
+    assert K.lib.last_algo() == "stream"
+    # strided views: a channel slice of a wider tensor still streams (16-byte aligned strides)
+    wide = torch.randn(4, 7, 256, 256, device="cuda") + 30.0
+    v = wide[:, 1:6]
+    d = K.ops.degrade_batch(v, kd, factor=8)
+    assert K.lib.last_algo() == "tma"
+    assert torch.equal(d, K.ops.degrade_batch(v.contiguous(), kd, factor=8))
