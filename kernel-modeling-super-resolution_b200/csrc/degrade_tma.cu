@@ -462,6 +462,7 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
             }
         };
 
+
         int i = 0;
 #pragma unroll 1
         while (i < nsteps) {
