@@ -15,7 +15,7 @@ namespace kmsr {
 __global__ void __launch_bounds__(128)
 prepare_kernels_kernel(const float* __restrict__ kbank, int kh, int kw, int fold, int KH, int KW,
                        int KWp, float* __restrict__ comp, float* __restrict__ dsum) {
-    extern __shared__ float kn[];           // kh*kw normalised taps
+    extern __shared__ __align__(16) float kn[];   // kh*kw normalised taps, then the fp64 horizontal sums
     __shared__ double red[128];
     const int kc = blockIdx.x;
     const float* k = kbank + (size_t)kc * kh * kw;
@@ -48,6 +48,20 @@ prepare_kernels_kernel(const float* __restrict__ kbank, int kh, int kw, int fold
     }
     if (threadIdx.x == 0) dsum[kc] = (float)(red[0] - 1.0);
 
+    // box fold, separable: horizontal running sums of the normalised taps (fp64), then vertical sums of those --
+    // fold + fold additions per composite tap instead of fold * fold (what made a per-patch bank of 4096 x 5
+    // kernels cost a fifth of the degrade pass)
+    double* hs = reinterpret_cast<double*>(kn + ((taps + 1) & ~1));      // [kh][KW] horizontal sums
+    for (int i = threadIdx.x; i < kh * KW; i += blockDim.x) {
+        const int r = i / KW, v = i % KW;
+        double acc = 0.0;
+        for (int b = 0; b < fold; ++b) {
+            const int kx = v - b;
+            if (kx >= 0 && kx < kw) acc += (double)kn[r * kw + kx];
+        }
+        hs[i] = acc;
+    }
+    __syncthreads();
     const double inv = 1.0 / ((double)fold * (double)fold);
     float* out = comp + (size_t)kc * KH * KWp;
     for (int i = threadIdx.x; i < KH * KWp; i += blockDim.x) {
@@ -56,12 +70,7 @@ prepare_kernels_kernel(const float* __restrict__ kbank, int kh, int kw, int fold
         if (v < KW) {
             for (int a = 0; a < fold; ++a) {
                 const int ky = u - a;
-                if (ky < 0 || ky >= kh) continue;
-                for (int b = 0; b < fold; ++b) {
-                    const int kx = v - b;
-                    if (kx < 0 || kx >= kw) continue;
-                    acc += (double)kn[ky * kw + kx];
-                }
+                if (ky >= 0 && ky < kh) acc += hs[ky * KW + v];
             }
         }
         out[i] = (float)(acc * inv);
@@ -77,12 +86,13 @@ int launch_prepare(const float* kbank, long long nK, int C, int kh, int kw, int 
     KMSR_REQUIRE(nK >= 0 && C >= 1, KMSR_E_INVALID, "prepare_kernels: nK=%lld C=%d", nK, C);
     if (nK == 0) return KMSR_OK;
     KMSR_REQUIRE(kbank && comp && dsum, KMSR_E_INVALID, "prepare_kernels: null pointer");
-    KMSR_REQUIRE((size_t)kh * kw * sizeof(float) <= 48 * 1024, KMSR_E_UNSUPPORTED,
+    const size_t smem = (size_t)((kh * kw + 1) & ~1) * sizeof(float) + (size_t)kh * g.KW * sizeof(double);
+    KMSR_REQUIRE(smem <= 48 * 1024, KMSR_E_UNSUPPORTED,
                  "prepare_kernels: kernel %dx%d exceeds 48 KB of shared memory", kh, kw);
     const int fold = down_mode == KMSR_DOWN_BOXMEAN ? g.stride : 1;
     const long long blocks = nK * C;
     KMSR_REQUIRE(blocks < (1ll << 31), KMSR_E_INVALID, "prepare_kernels: nK*C too large");
-    prepare_kernels_kernel<<<(unsigned)blocks, 128, (size_t)kh * kw * sizeof(float), st>>>(
+    prepare_kernels_kernel<<<(unsigned)blocks, 128, smem, st>>>(
         kbank, kh, kw, fold, g.KH, g.KW, g.KWp, comp, dsum);
     KMSR_LAUNCH_CHECK("prepare_kernels_kernel");
     return KMSR_OK;

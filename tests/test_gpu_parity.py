@@ -599,3 +599,27 @@ def test_shapes_the_streaming_kernels_hand_to_each_other(K, synth, bank):
     d = K.ops.degrade_batch(v, kd, factor=8)
     assert K.lib.last_algo() == "tma"
     assert torch.equal(d, K.ops.degrade_batch(v.contiguous(), kd, factor=8))
+
+
+def test_host_buffer_pipeline_equals_device_path(K, synth, bank):
+    """pipeline.PairSynthesizer.run_host (chunked, double-buffered H2D / kernel / D2H over three streams) returns the
+    bits of the one-launch device path, also when the batch is not a multiple of the chunk; synthesize_pairs draws
+    the same indices as the oracle's composition."""
+    from kmsr_b200 import pipeline
+    kb, sb = bank
+    n = 37
+    hr = np.concatenate([synth.make_hr(20, 3500, "textured"), synth.make_hr(17, 3501, "water")])
+    pool = synth.make_noise_pool(128, 42)
+    kidx, nidx = K.rng.draw_multi_kernel_indices(n, 10, 128, 7)
+    syn = pipeline.PairSynthesizer(kb, sb, pool, factor=8, chunk=8)
+    dev = syn.run_device(torch.from_numpy(hr).cuda(), kidx, nidx).cpu()
+    host_in = torch.from_numpy(hr).pin_memory()
+    for _ in range(2):                                   # second pass reuses the staging buffers
+        out = syn.run_host(host_in, kidx, nidx)
+        torch.cuda.synchronize()
+        assert torch.equal(out, dev)
+    lr, k2, n2 = pipeline.synthesize_pairs(hr, kb, sb, pool, seed=7, factor=8, chunk=16)
+    assert np.array_equal(k2, kidx) and np.array_equal(n2, nidx) and torch.equal(lr, dev)
+    ref = orc.multi_kernel_pairs(hr[:4], kb, sb, pool, kidx[:4], nidx[:4], 8)
+    for i in range(4):
+        check_pixels(dev[i].numpy(), ref[i], hr[i], name=f"pipeline {i}")
