@@ -210,6 +210,16 @@ KMSR_API int kmsr_keep_mask(const float* masked, int C, int H, int W, int P, int
                             double nan_threshold, uint8_t* keep, int32_t* nan_count,
                             void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Keep grid of the masked scene computed straight from the RAW scene: nothing is written, the scene is read once.
+ * Same result as kmsr_water_mask followed by kmsr_keep_mask.  With nan_threshold = 0 (the reference's value,
+ * CUT:31) a kept window contains no masked pixel, so its pixels ARE the raw scene's and kmsr_degrade_windows can
+ * run on the raw scene: the masked copy of A_00_patch_cutter_universal.py:112-113 is never materialised.
+ * Needs P % stride == 0 (KMSR_E_UNSUPPORTED otherwise); workspace: kmsr_keep_mask_workspace_bytes(H, W, P, stride). */
+KMSR_API int kmsr_scene_keep_mask(const float* data, int C, int H, int W, int nir, float invalid,
+                                  float tmin, float tmax, int P, int stride, double nan_threshold,
+                                  uint8_t* keep, int32_t* nan_count,
+                                  void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------
  * Launch counter: number of kernels this library launched on the calling process since load.   */
 KMSR_API int64_t kmsr_launch_count(void);

@@ -74,6 +74,23 @@ def create_patches(data, patch_size: int = PATCH_SIZE, stride_ratio: float = STR
     return total, int(ij.shape[0]), ij.cpu().numpy(), offsets, scene
 
 
+def create_patches_from_raw(raw, threshold_min: float = THRESHOLD_MIN, threshold_max: float = THRESHOLD_MAX,
+                            patch_size: int = PATCH_SIZE, stride_ratio: float = STRIDE_RATIO):
+    """process_single_nc's mask + tiling (CUT:89-123, :152-183) fused for the reference's nan_threshold = 0: the keep
+    grid comes from one read of the RAW scene and the kept windows -- which contain no masked pixel, hence equal the
+    raw pixels -- are returned as offsets into the raw scene itself: (total, kept, ij, offsets, scene_device).
+    Nothing is written, the masked copy is never materialised."""
+    ops.require_cuda()
+    t = raw if isinstance(raw, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(raw, dtype=np.float32))
+    scene = t.cuda().contiguous() if not t.is_cuda else t.contiguous()
+    _, h, w = scene.shape
+    hp, wp, stride = patch_grid(h, w, patch_size, stride_ratio)
+    keep, _ = ops.scene_keep_mask(scene, threshold_min, threshold_max, patch_size, stride, 0.0, NIR_BAND_INDEX, INVALID_VALUE)
+    ij = torch.nonzero(keep)
+    offsets = (ij[:, 0] * stride * w + ij[:, 1] * stride).to(torch.int64)
+    return max(hp, 0) * max(wp, 0), int(ij.shape[0]), ij.cpu().numpy(), offsets, scene
+
+
 def save_patch_as_nc(patch: np.ndarray, output_path: str, metadata: dict, grid_i: int, grid_j: int, h_offset: int,
                      w_offset: int) -> None:
     """CUT:200-260: one patch file with groups geophysical_data (one variable per band) and navigation_data

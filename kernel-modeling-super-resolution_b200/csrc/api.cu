@@ -30,6 +30,8 @@ int launch_water_mask(float*, int, long long, int, float, float, float, float*, 
 int launch_stats_finish(const double*, const float*, long long, int, long long, long long, double*, double*,
                         double*, cudaStream_t);
 long long keep_mask_workspace(int, int, int, int);
+int launch_scene_keep_mask(const float*, int, int, int, int, float, float, float, int, int, double, unsigned char*,
+                           int*, void*, long long, cudaStream_t);
 int launch_keep_mask(const float*, int, int, int, int, int, double, unsigned char*, int*, void*,
                      long long, cudaStream_t);
 
@@ -278,6 +280,17 @@ KMSR_API int kmsr_water_mask(float* data, int C, int64_t hw, int nir, float inva
 
 KMSR_API int64_t kmsr_keep_mask_workspace_bytes(int H, int W, int P, int stride) {
     return keep_mask_workspace(H, W, P, stride);
+}
+
+KMSR_API int kmsr_scene_keep_mask(const float* data, int C, int H, int W, int nir, float invalid, float tmin,
+                                  float tmax, int P, int stride, double nan_threshold, uint8_t* keep,
+                                  int32_t* nan_count, void* workspace, int64_t workspace_bytes, void* stream) {
+    KMSR_REQUIRE(C >= 1 && H >= 0 && W >= 0 && P >= 1 && stride >= 1 && nir >= 0 && nir < C, KMSR_E_INVALID,
+                 "scene_keep_mask: C=%d H=%d W=%d P=%d stride=%d nir=%d", C, H, W, P, stride, nir);
+    if (H < P || W < P) return KMSR_OK;
+    KMSR_REQUIRE(data && keep, KMSR_E_INVALID, "scene_keep_mask: null pointer");
+    return launch_scene_keep_mask(data, C, H, W, nir, invalid, tmin, tmax, P, stride, nan_threshold, keep, nan_count,
+                                  workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 KMSR_API int kmsr_keep_mask(const float* masked, int C, int H, int W, int P, int stride, double nan_threshold,

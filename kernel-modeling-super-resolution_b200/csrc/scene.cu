@@ -118,6 +118,56 @@ nan_cells_kernel(const float* __restrict__ masked, int C, int H, int W, int cell
     }
 }
 
+// stage 1 without a materialised mask: the NaN count the masked scene WOULD have in every cell, straight from the
+// raw scene -- a pixel of band c is NaN iff NIR is fill / NaN / outside [tmin, tmax] (CUT:108-113) or the band
+// value itself is fill (CUT:102) or NaN.  With the reference's nan_threshold = 0 a kept window holds no masked
+// pixel, so its pixels equal the raw scene's and the degrade kernel can read the raw scene directly.
+__global__ void __launch_bounds__(256)
+scene_cells_kernel(const float* __restrict__ data, int C, int H, int W, int nir, float invalid, float tmin,
+                   float tmax, int cell, int ch, int cw, int* __restrict__ cells) {
+    __shared__ int red[8];
+    const int cj = blockIdx.x % cw, ci = blockIdx.x / cw;
+    const int y0 = ci * cell, x0 = cj * cell;
+    const int hh = min(cell, H - y0), ww = min(cell, W - x0);
+    const long long plane = (long long)H * W;
+    int cnt = 0;
+    auto bad = [&](float n) { return !((n != invalid) && (n >= tmin) && (n <= tmax)); };
+    if ((W & 3) == 0 && (x0 & 3) == 0 && (ww & 3) == 0 && (((uintptr_t)data) & 15) == 0 && (ww >> 2) <= 256) {
+        const int w4 = ww >> 2, per_it = 256 / w4;
+        const int lx = threadIdx.x % w4, lr = threadIdx.x / w4;
+        if (lr < per_it) {
+            for (int y = lr; y < hh; y += per_it) {
+                const float* px = data + (long long)(y0 + y) * W + x0 + 4 * lx;
+                const float4 n = *reinterpret_cast<const float4*>(px + (long long)nir * plane);
+                const bool b0 = bad(n.x), b1 = bad(n.y), b2 = bad(n.z), b3 = bad(n.w);
+                for (int c = 0; c < C; ++c) {
+                    const float4 v = c == nir ? n : *reinterpret_cast<const float4*>(px + (long long)c * plane);
+                    cnt += (b0 || v.x == invalid || v.x != v.x) + (b1 || v.y == invalid || v.y != v.y) +
+                           (b2 || v.z == invalid || v.z != v.z) + (b3 || v.w == invalid || v.w != v.w);
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < hh * ww; i += blockDim.x) {
+            const float* px = data + (long long)(y0 + i / ww) * W + x0 + (i % ww);
+            const bool b = bad(px[(long long)nir * plane]);
+            for (int c = 0; c < C; ++c) {
+                const float v = px[(long long)c * plane];
+                cnt += (b || v == invalid || v != v);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        cells[blockIdx.x] = t;
+    }
+}
+
 // stage 2: window (i,j) covers (P/cell)^2 cells
 __global__ void keep_from_cells_kernel(const int* __restrict__ cells, int cw, int per, int hp, int wp,
                                        long long limit, unsigned char* __restrict__ keep,
@@ -191,16 +241,39 @@ long long keep_mask_workspace(int H, int W, int P, int stride) {
     return ch * cw * (long long)sizeof(int);
 }
 
+// CUT:179-183: drop iff nan_ratio > thr  <=>  keep iff count <= floor(thr * total) (exact in fp64 here)
+static long long keep_limit(int C, int P, double thr) {
+    const double total = (double)C * P * P;
+    long long limit = thr >= 1.0 ? (long long)total : (long long)floor(thr * total);
+    while (limit < (long long)total && (double)(limit + 1) / total <= thr) ++limit;
+    while (limit >= 0 && (double)limit / total > thr) --limit;
+    return limit;
+}
+
+int launch_scene_keep_mask(const float* data, int C, int H, int W, int nir, float invalid, float tmin, float tmax,
+                           int P, int stride, double thr, unsigned char* keep, int* nan_count, void* ws,
+                           long long ws_bytes, cudaStream_t st) {
+    if (H < P || W < P) return KMSR_OK;
+    KMSR_REQUIRE(P % stride == 0, KMSR_E_UNSUPPORTED,
+                 "scene_keep_mask: patch size %d is not a multiple of the stride %d (use water_mask + keep_mask)", P, stride);
+    const int hp = (H - P) / stride + 1, wp = (W - P) / stride + 1;
+    const int ch = (H + stride - 1) / stride, cw = (W + stride - 1) / stride;
+    KMSR_REQUIRE(ws && ws_bytes >= (long long)ch * cw * (long long)sizeof(int), KMSR_E_INVALID,
+                 "scene_keep_mask: workspace of %lld B needed", (long long)ch * cw * (long long)sizeof(int));
+    scene_cells_kernel<<<ch * cw, 256, 0, st>>>(data, C, H, W, nir, invalid, tmin, tmax, stride, ch, cw, (int*)ws);
+    KMSR_LAUNCH_CHECK("scene_cells_kernel");
+    keep_from_cells_kernel<<<(hp * wp + 127) / 128, 128, 0, st>>>((const int*)ws, cw, P / stride, hp, wp,
+                                                                  keep_limit(C, P, thr), keep, nan_count);
+    KMSR_LAUNCH_CHECK("keep_from_cells_kernel");
+    return KMSR_OK;
+}
+
 int launch_keep_mask(const float* masked, int C, int H, int W, int P, int stride, double thr,
                      unsigned char* keep, int* nan_count, void* ws, long long ws_bytes,
                      cudaStream_t st) {
     if (H < P || W < P) return KMSR_OK;
     const int hp = (H - P) / stride + 1, wp = (W - P) / stride + 1;
-    // CUT:179-183: drop iff nan_ratio > thr  <=>  keep iff count <= floor(thr * total) (exact in fp64 here)
-    const double total = (double)C * P * P;
-    long long limit = thr >= 1.0 ? (long long)total : (long long)floor(thr * total);
-    while (limit < (long long)total && (double)(limit + 1) / total <= thr) ++limit;
-    while (limit >= 0 && (double)limit / total > thr) --limit;
+    const long long limit = keep_limit(C, P, thr);
     if (P % stride == 0) {
         const int ch = (H + stride - 1) / stride, cw = (W + stride - 1) / stride;
         KMSR_REQUIRE(ws && ws_bytes >= (long long)ch * cw * (long long)sizeof(int), KMSR_E_INVALID,

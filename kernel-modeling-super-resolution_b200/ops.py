@@ -289,3 +289,26 @@ def keep_mask(masked: torch.Tensor, patch_size: int = 256, stride: int = 128, na
             L.check(L.lib().kmsr_keep_mask(_ptr(masked), Cc, H, W, patch_size, stride, float(nan_threshold),
                                            _ptr(keep), _ptr(cnt), _ptr(ws), wsb, _stream(dev)))
     return keep.bool(), cnt
+
+
+def scene_keep_mask(scene: torch.Tensor, tmin: float, tmax: float, patch_size: int = 256, stride: int = 128,
+                    nan_threshold: float = 0.0, nir: int = 4, invalid: float = -9999.0):
+    """keep[i,j] / NaN count of every window of the masked scene, computed from the RAW scene [C,H,W] in one read
+    (no masked copy, no in-place fill replacement).  With nan_threshold == 0 the kept windows can be degraded
+    straight from `scene` (A_00_patch_cutter_universal.py:89-123 + :152-183 fused)."""
+    require_cuda()
+    assert scene.is_cuda and scene.is_contiguous() and scene.dtype == torch.float32
+    dev = scene.device
+    Cc, H, W = scene.shape
+    hp = (H - patch_size) // stride + 1 if H >= patch_size else 0
+    wp = (W - patch_size) // stride + 1 if W >= patch_size else 0
+    keep = torch.zeros((max(hp, 0), max(wp, 0)), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros((max(hp, 0), max(wp, 0)), dtype=torch.int32, device=dev)
+    if hp > 0 and wp > 0:
+        wsb = int(L.lib().kmsr_keep_mask_workspace_bytes(H, W, patch_size, stride))
+        ws = torch.empty(max(wsb, 4), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.lib().kmsr_scene_keep_mask(_ptr(scene), Cc, H, W, nir, float(invalid), float(tmin), float(tmax),
+                                                 patch_size, stride, float(nan_threshold), _ptr(keep), _ptr(cnt), _ptr(ws),
+                                                 wsb, _stream(dev)))
+    return keep.bool(), cnt

@@ -623,3 +623,33 @@ def test_host_buffer_pipeline_equals_device_path(K, synth, bank):
     ref = orc.multi_kernel_pairs(hr[:4], kb, sb, pool, kidx[:4], nidx[:4], 8)
     for i in range(4):
         check_pixels(dev[i].numpy(), ref[i], hr[i], name=f"pipeline {i}")
+
+
+def test_raw_scene_keep_grid_and_windows(K, golden, synth, bank):
+    """kmsr_scene_keep_mask: the keep grid / NaN counts from the RAW scene equal water_mask + keep_mask (and the
+    oracle); at nan_threshold 0 the kept windows degraded straight from the raw scene equal the masked ones bitwise."""
+    kb, _ = bank
+    scene = synth.make_scene(21, 896, 1152, n_fill=3, n_cloud=3)
+    scene[2, 300:310, 400:420] = np.nan                    # a NaN that is not a fill value
+    scene[0, 700, 100] = -9999.0                           # fill in one band only
+    raw = torch.from_numpy(scene).cuda()
+    masked_ref = orc.apply_water_mask(scene.copy(), 1e-6, 7.0)
+    for thr in (0.0, 0.01):
+        keep, cnt = K.ops.scene_keep_mask(raw, 1e-6, 7.0, 256, 128, thr)
+        work = raw.clone()
+        masked = K.ops.water_mask(work, 1e-6, 7.0)
+        keep2, cnt2 = K.ops.keep_mask(masked, 256, 128, thr)
+        assert torch.equal(keep, keep2) and torch.equal(cnt, cnt2)
+        assert np.array_equal(keep.cpu().numpy(), orc.keep_mask(masked_ref, 256, 0.5, thr))
+    assert torch.equal(raw, torch.from_numpy(scene).cuda()) or bool(torch.isnan(raw).any())     # the raw scene is not modified
+    total, kept, ij, offs, dev_scene = K.CUT.create_patches_from_raw(scene)
+    t2, k2, ij2, offs2, dev_masked = K.CUT.create_patches(masked_ref, 256, 0.5, 0.0)
+    assert (total, kept) == (t2, k2) and np.array_equal(ij, ij2) and kept > 0
+    h, w = scene.shape[1:]
+    a = K.ops.degrade_batch(dev_scene, torch.from_numpy(kb[1]).cuda(), factor=8, patch_offsets=offs, patch_hw=(256, 256),
+                            strides=(h * w, w), scene_hw=(h, w), x_multiple=128)
+    b = K.ops.degrade_batch(dev_masked, torch.from_numpy(kb[1]).cuda(), factor=8, patch_offsets=offs2, patch_hw=(256, 256),
+                            strides=(h * w, w), scene_hw=(h, w), x_multiple=128)
+    assert K.lib.last_algo() == "tma" and torch.equal(a, b) and bool(torch.isfinite(a).all())
+    with pytest.raises(K.lib.KmsrError):
+        K.ops.scene_keep_mask(raw, 1e-6, 7.0, 96, 40, 0.0)            # P % stride != 0

@@ -251,6 +251,23 @@ def config4(args, rank, world, dev):
 
     ms = timed(run, args.reps, world, before=lambda: slab.copy_(raw))
 
+    # the reference's nan_threshold = 0 lets mask + tiling collapse into one read of the raw scene
+    # (kmsr_scene_keep_mask) with the kept windows degraded straight from it
+    fstate = {}
+
+    def run_fused():
+        keep, _ = ops.scene_keep_mask(raw, 1e-6, 7.0, P, stride, 0.0)
+        ij = torch.nonzero(keep)
+        offs = (ij[:, 0] * stride * W + ij[:, 1] * stride).to(torch.int64)
+        k = int(offs.numel())
+        nidx = torch.from_numpy(rng.draw_noise_indices(k, 4096, 42)).to(dev)
+        lr = ops.degrade_batch(raw, pb, pool=pool, nidx=nidx, factor=8, noise_mode="add", patch_offsets=offs,
+                               patch_hw=(P, P), strides=(sh * W, W), scene_hw=(sh, W), x_multiple=stride)
+        fstate.update(keep=keep, lr=lr, k=k)
+
+    ms_fused = timed(run_fused, args.reps, world)
+    assert torch.equal(fstate["keep"], state["keep"]) and torch.equal(fstate["lr"], state["lr"]), "fused scene path differs"
+
     def degrade_only():
         ops.degrade_batch(masked, pb, pool=pool, nidx=state["nidx"], factor=8, noise_mode="add",
                           patch_offsets=(state["ij"][:, 0] * stride * W + state["ij"][:, 1] * stride).to(torch.int64),
@@ -266,6 +283,7 @@ def config4(args, rank, world, dev):
     scene_bytes = 4 * C * H * W
     out = {"config": 4, "workload": f"A_00 tiling of a [5,{H},{W}] scene (stride 128) + degrade + noise on kept windows, {world} GPU(s)",
            "algo": algo_after, "candidates": hp * wp, "kept": kept, "ms_scene_total": ms, "ms_degrade_only": ms_deg,
+           "ms_scene_total_fused": ms_fused, "kept_pairs_per_s_total_fused": kept / (ms_fused * 1e-3),
            "kept_pairs_per_s_total": kept / (ms * 1e-3), "kept_pairs_per_s_degrade": kept / (ms_deg * 1e-3),
            "unique_bytes_gbs_degrade": (scene_bytes + kept * 2 * 4 * C * 1024) / (ms_deg * 1e-3) / 1e9,
            "patchwise_bytes_gbs_degrade": kept * (4 * C * P * P + 2 * 4 * C * 1024) / (ms_deg * 1e-3) / 1e9}
