@@ -653,3 +653,24 @@ def test_raw_scene_keep_grid_and_windows(K, golden, synth, bank):
     assert K.lib.last_algo() == "tma" and torch.equal(a, b) and bool(torch.isfinite(a).all())
     with pytest.raises(K.lib.KmsrError):
         K.ops.scene_keep_mask(raw, 1e-6, 7.0, 96, 40, 0.0)            # P % stride != 0
+
+
+def test_content_adaptive_pick_feeds_the_fused_kernel(K, golden, synth, bank):
+    """f2 on the device: selector logits (cuDNN fp32, TF32 off) equal the reference's, the argmax pick drives the
+    fused degrade + sigma-noise launch, and the result equals the oracle composition with the same picks."""
+    from kmsr_b200.selector import Selector, degrade_content_adaptive
+    kb, sb = bank
+    z = golden("selector.npz")
+    sel = Selector.from_npz(z, "cuda")
+    hr = np.concatenate([synth.make_hr(4, 5100, "textured"), synth.make_hr(2, 5101, "water")])
+    lg = sel.logits(torch.from_numpy(hr).cuda()).cpu().numpy()
+    assert np.abs(lg - z["logits"][:6]).max() <= 1e-4 * np.abs(z["logits"]).max()
+    pool = synth.make_noise_pool(64, 42)
+    lr, kidx, nidx = degrade_content_adaptive(torch.from_numpy(hr), sel, kb, sb, pool, seed=42)
+    assert np.array_equal(kidx, z["argmax"][:6]) and K.lib.last_algo() == "tma"
+    _, n_ref = K.rng.draw_multi_kernel_indices(6, 10, 64, 42)
+    assert np.array_equal(nidx, n_ref)
+    ref = orc.multi_kernel_pairs(hr, kb, sb, pool, kidx, nidx, 8)
+    for i in range(6):
+        ex = exact_degrade(hr[i], kb[kidx[i]], 8)
+        check_pixels(lr[i].numpy(), ref[i], hr[i], ex, noise=sb[kidx[i]][:, None, None].astype(np.float64) * pool[nidx[i]], name=f"adaptive {i}")

@@ -226,3 +226,20 @@ def test_patch_io_roundtrip_and_listing(tmp_path):
         (tmp_path / "z.nc").write_bytes(b"CDF")
         with pytest.raises(ImportError):
             pio.read_group_bands(str(tmp_path / "z.nc"), "denoised")
+
+
+def test_selector_logits_match_the_reference_model(golden, synth):
+    """f2: SelectorNet inference (train_gemini.py:14-39, eval mode) from the shipped moe_model.pth weights against the
+    logits the reference module produced (tests/golden/make_selector_golden.py); hard pick = argmax."""
+    from kmsr_b200.selector import Selector
+    z = golden("selector.npz")
+    sel = Selector.from_npz(z)
+    hr = np.concatenate([synth.make_hr(4, 5100, "textured"), synth.make_hr(2, 5101, "water")])
+    got = torch.cat([sel.logits(torch.from_numpy(hr)), sel.logits(torch.from_numpy(z["small_inputs"]))]).numpy()
+    ref = z["logits"]
+    assert got.shape == ref.shape == (18, 10)
+    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.array_equal(got.argmax(axis=1), z["argmax"])
+    # the bank the reference model derives from its parameters is the shipped moe_kernels bank
+    bank = golden("moe_bank.npz")
+    assert np.abs(z["kernels"] - bank["kernels"]).max() <= 1e-8 and np.abs(z["sigmas"] - bank["sigmas"]).max() <= 2e-7
