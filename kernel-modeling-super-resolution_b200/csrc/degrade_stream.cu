@@ -34,6 +34,8 @@ constexpr int kThreadsS = (kConsumers + kProducers) * 32;
 constexpr int kTX = 4;                         // LR columns per lane
 constexpr int kRenameQ = 5;                    // accumulator sets are renamed (steps unrolled by Q) up to this many; 6..8 measured 4-9 % slower (code size)
 
+constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+
 template <int K, int S>
 struct Cfg {
     static constexpr int KW = K + S - 1;                         // composite taps per row / column
@@ -49,6 +51,10 @@ struct Cfg {
     static constexpr int TP = KW / 2;                            // tap pairs
     static constexpr int WP = ((KW + 3) / 4 * 4 / 4) % 2 ? (KW + 3) / 4 * 4 : (KW + 3) / 4 * 4 + 4;   // weight row pitch, /4 odd
     static constexpr int WROWS = Q * S;                          // rows >= KW are zero
+    // steps unrolled with renamed accumulator sets: all Q when Q <= kRenameQ, else none (one in-place rotation per
+    // step): unrolling 2 or 4 steps of the larger shapes was measured 3-9 % slower (code size), r49
+    static constexpr int U = Q <= kRenameQ ? Q : 1;
+    static constexpr int GC = cgcd(Q, U);                        // cycles of the rotation by U
     static_assert(K % 2 == 1 && (S == 2 || S == 4 || S == 8), "odd kernel, factor 2/4/8");
 };
 
@@ -241,8 +247,7 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
         const float* nzp = nz + col0 + ox;
         const int lane_off = G::GW * g;
 
-        // One step.  SH = i mod Q when the accumulator sets are renamed (Q <= kRenameQ: set j holds output rows
-        // Y == j mod Q), SH = -1 when they are rotated by value (set q holds output row i - q).
+        // One step.  SH = position of the step inside its unrolled block: the set of output row i - q is (SH - q) mod Q.
         auto step = [&](auto sh_tag, const int i) {
             constexpr int SH = decltype(sh_tag)::value;
             // ---- rows this step needs: padded rows S*i .. S*i+S-1 = image rows S*i - PAD + ly ----
@@ -328,7 +333,7 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
 #pragma unroll
             for (int q = 0; q < G::Q; ++q) {
                 constexpr int dummy = 0; (void)dummy;
-                const int j = SH < 0 ? q : (SH - q + G::Q) % G::Q;          // accumulator set of output row i - q
+                const int j = (SH - q + G::Q) % G::Q;                       // accumulator set of output row i - q
                 const int u = ly + S * q;
                 const float* wrow = wsm + u * G::WP;
                 u64 T[kTX];
@@ -351,7 +356,7 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
             }
 
             // ---- the oldest set completes: reduce over the S row lanes, epilogue, store ----
-            constexpr int JO = SH < 0 ? G::Q - 1 : (SH + 1) % G::Q;         // == (SH - (Q-1)) mod Q
+            constexpr int JO = (SH + 1) % G::Q;                             // == (SH - (Q-1)) mod Q
             if (Y >= 0) {
                 float v[kTX];
 #pragma unroll
@@ -385,26 +390,35 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
                     }
                 }
             }
-            if (SH < 0) {
-                // rotate the accumulator sets by value: set q becomes set q + 1, set 0 starts empty
 #pragma unroll
-                for (int q = G::Q - 1; q > 0; --q)
-#pragma unroll
-                    for (int x = 0; x < kTX; ++x) A[q][x] = A[q - 1][x];
-#pragma unroll
-                for (int x = 0; x < kTX; ++x) A[0][x] = 0ull;
-            } else {
-#pragma unroll
-                for (int x = 0; x < kTX; ++x) A[JO][x] = 0ull;             // becomes the fresh set of step i + 1
-            }
+            for (int x = 0; x < kTX; ++x) A[JO][x] = 0ull;                 // becomes the fresh set of step i + 1
         };
 
-        if constexpr (G::Q <= kRenameQ) {
+        // U consecutive steps run with compile-time set indices (renaming); when U < Q the sets are then rotated by U
+        // positions by value, once per U steps instead of once per step
 #pragma unroll 1
-            for (int i = 0; i < nsteps; i += G::Q) Unroll<0, G::Q>::run(step, i, nsteps);
-        } else {
-#pragma unroll 1
-            for (int i = 0; i < nsteps; ++i) step(std::integral_constant<int, -1>{}, i);
+        for (int i = 0; i < nsteps; i += G::U) {
+            Unroll<0, G::U>::run(step, i, nsteps);
+            if constexpr (G::U != G::Q) {
+                // in-place rotation A[m] <- A[(m + U) mod Q]: gcd(Q, U) cycles, one spare set
+                constexpr int GC = G::GC;
+#pragma unroll
+                for (int c0 = 0; c0 < GC; ++c0) {
+                    u64 T[kTX];
+#pragma unroll
+                    for (int x = 0; x < kTX; ++x) T[x] = A[c0][x];
+                    int cur = c0;
+#pragma unroll
+                    for (int t = 0; t < G::Q / GC - 1; ++t) {
+                        const int nxt = (cur + G::U) % G::Q;
+#pragma unroll
+                        for (int x = 0; x < kTX; ++x) A[cur][x] = A[nxt][x];
+                        cur = nxt;
+                    }
+#pragma unroll
+                    for (int x = 0; x < kTX; ++x) A[cur][x] = T[x];
+                }
+            }
         }
         if (a.wbuf == 2) {
             wcur ^= 1;
