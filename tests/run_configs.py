@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """BASELINE.json configs 1, 3, 4, 5 on the GPU (config 2 is bench.py): parity + throughput per config.
 
-    python tools/run_configs.py --configs 1,3,4,5 [--out gpurun_out/configs.json]
-    python -m torch.distributed.run --nproc-per-node N ... tools/run_configs.py --configs 3,4   # sharded
+    python tests/run_configs.py --configs 1,3,4,5 [--out gpurun_out/configs.json]
+    python -m torch.distributed.run --nproc-per-node N ... tests/run_configs.py --configs 3,4   # sharded
 
 One JSON object per config on stdout (rank 0) and all of them in --out.  Timing: CUDA events on the current
 stream, best of `--reps` after one warm-up, max over ranks.  The oracle (tests' checker) is used here only to
-verify samples of what the GPU produced; this is a measurement script, not part of the product.
+verify samples of what the GPU produced; this is a measurement + parity script (it lives under tests/ because it
+uses the oracle), not part of the product.
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # tests/ may use the oracle as a checker
 sys.path.insert(0, ROOT)
 
 import kmsr_b200.synth as synth  # noqa: E402
