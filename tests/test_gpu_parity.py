@@ -674,3 +674,20 @@ def test_content_adaptive_pick_feeds_the_fused_kernel(K, golden, synth, bank):
     for i in range(6):
         ex = exact_degrade(hr[i], kb[kidx[i]], 8)
         check_pixels(lr[i].numpy(), ref[i], hr[i], ex, noise=sb[kidx[i]][:, None, None].astype(np.float64) * pool[nidx[i]], name=f"adaptive {i}")
+
+
+@pytest.mark.parametrize("h,w,k,s,algo", [(64, 256, 13, 8, "tma"), (8, 256, 13, 8, "tma"), (16, 256, 13, 8, "tma"), (248, 256, 13, 8, "tma"),
+                                          (96, 128, 11, 4, "stream"), (8, 64, 15, 8, "stream"), (40, 512, 21, 2, "stream"),
+                                          (24, 768, 13, 8, "stream")])
+def test_non_square_and_short_patches(K, synth, bank, h, w, k, s, algo):
+    """Rectangular / very short patches through the streaming kernels (few steps per band, rings barely filled)."""
+    kb, _ = bank
+    kern = kb[3] if k == 13 else synth.softmax_kernels(k, 5)
+    n = 5
+    rs = np.random.RandomState(h * 1000 + w)
+    hr = (rs.standard_normal((n, 5, h, w)) * 3.0 + np.array([80, 70, 50, 25, 8])[None, :, None, None]).astype(np.float32)
+    lr = K.ops.degrade_batch(torch.from_numpy(hr).cuda(), torch.from_numpy(kern).cuda(), factor=s, algo=algo).cpu().numpy()
+    assert K.lib.last_algo() == algo and lr.shape == (n, 5, h // s, w // s)
+    for i in range(n):
+        ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kern), s).numpy()
+        check_pixels(lr[i], ref, hr[i], exact_degrade(hr[i], kern, s), name=f"{h}x{w} k{k} s{s} #{i}")
