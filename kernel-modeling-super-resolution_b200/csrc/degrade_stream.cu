@@ -31,16 +31,18 @@ namespace {
 constexpr int kConsumers = 8;                  // consumer warps per CTA
 constexpr int kProducers = 4;                  // producer warps (one elected thread each)
 constexpr int kThreadsS = (kConsumers + kProducers) * 32;
-constexpr int kTX = 4;                         // LR columns per lane
+constexpr bool kWide4 = true;                  // factor 4, 256-wide blocks: 8 LR columns per lane (one warp per block row)
 constexpr int kRenameQ = 5;                    // accumulator sets are renamed (steps unrolled by Q) up to this many; 6..8 measured 4-9 % slower (code size)
 
 constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 
-template <int K, int S>
+template <int K, int S, int TX>
 struct Cfg {
+    static constexpr int kTX = TX;                               // LR columns per lane
     static constexpr int KW = K + S - 1;                         // composite taps per row / column
     static constexpr int PAD = K / 2;
     static constexpr int Q = (KW + S - 1) / S;                   // live output rows per lane
+    static constexpr int NV = TX >= S ? TX / S : 1;               // outputs a lane writes per step after the reduce-scatter
     static constexpr int GW = kTX * S;                           // input columns per lane group
     static constexpr int GX = 32 / S;                            // groups per warp
     static constexpr int AL = (PAD + 3) / 4 * 4;                 // staged columns left of the block (16-byte aligned)
@@ -99,10 +101,11 @@ struct StreamArgs {
     int wbuf;               // weight buffers per warp: 2 = the next band's kernel is prefetched, 1 = staged between bands
 };
 
-template <int K, int S>
+template <int K, int S, int TX>
 __global__ void __launch_bounds__(kThreadsS, 1)
 degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs a) {
-    using G = Cfg<K, S>;
+    using G = Cfg<K, S, TX>;
+    constexpr int kTX = TX;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = a.depth;
@@ -241,8 +244,8 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
 
         // output columns after the reduce-scatter over the S row lanes
         const int col0 = it.blk * (a.BW / S) + kTX * g;       // first LR column of this lane group
-        const int ox = S == 8 ? (ly >> 1) : (S == 4 ? ly : 2 * ly);
-        const bool writer = lane_on && (S != 8 || (ly & 1) == 0);
+        const int ox = kTX >= S ? (kTX / S) * ly : ly / (S / kTX);
+        const bool writer = lane_on && (kTX >= S || (ly & (S / kTX - 1)) == 0);
         float* outp = a.lr + it.band * ohw + col0 + ox;
         const float* nzp = nz + col0 + ox;
         const int lane_off = G::GW * g;
@@ -287,11 +290,9 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
             }
             // noise of the row that completes in this step: issue the load before the arithmetic
             const int Y = i - (G::Q - 1);
-            float nzv[2] = {0.0f, 0.0f};
-            if (noisy && writer && Y >= 0) {
-                nzv[0] = __ldg(nzp + (long long)Y * a.Wo);
-                if (S == 2) nzv[1] = __ldg(nzp + (long long)Y * a.Wo + 1);
-            }
+            float nzv[G::NV];
+#pragma unroll
+            for (int j = 0; j < G::NV; ++j) nzv[j] = (noisy && writer && Y >= 0) ? __ldg(nzp + (long long)Y * a.Wo + j) : 0.0f;
 
             // d[j] = pixel column GW*g - PAD + j of the block, j < SEG
             float d[G::SEG];
@@ -361,32 +362,34 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
                 float v[kTX];
 #pragma unroll
                 for (int x = 0; x < kTX; ++x) v[x] = lo2(A[JO][x]) + hi2(A[JO][x]);
-                float r0, r1 = 0.0f;
-                {
-                    const bool up = (ly & (S / 2)) != 0;
-                    float k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];
-                    const float s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];
-                    k0 += __shfl_xor_sync(0xffffffffu, s0, S / 2);
-                    k1 += __shfl_xor_sync(0xffffffffu, s1, S / 2);
-                    r0 = k0; r1 = k1;
+                // reduce-scatter over the S row lanes: each stage halves the values a lane keeps (upper half for the
+                // lanes with the stage bit set) until one is left, the remaining stages are plain pair sums
+                int nv = kTX;
+#pragma unroll
+                for (int b = S / 2; b >= 1; b >>= 1) {
+                    if (nv > 1) {
+                        const bool up = (ly & b) != 0;
+                        const int half = nv / 2;
+#pragma unroll
+                        for (int j = 0; j < kTX / 2; ++j) {
+                            if (j < half) {
+                                const float keep = up ? v[half + j] : v[j];
+                                const float send = up ? v[j] : v[half + j];
+                                v[j] = keep + __shfl_xor_sync(0xffffffffu, send, b);
+                            }
+                        }
+                        nv = half;
+                    } else {
+                        v[0] += __shfl_xor_sync(0xffffffffu, v[0], b);
+                    }
                 }
-                if (S >= 4) {
-                    const bool up = (ly & (S / 4)) != 0;
-                    float k = up ? r1 : r0;
-                    const float sx = up ? r0 : r1;
-                    k += __shfl_xor_sync(0xffffffffu, sx, S / 4);
-                    r0 = k;
-                }
-                if (S == 8) r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
                 if (writer) {
                     float* out = outp + (long long)Y * a.Wo;
-                    float res = pv + fmaf(pv, ds, r0);
-                    if (noisy) res = fmaf(scale, nzv[0], res);
-                    out[0] = res;
-                    if (S == 2) {
-                        float res1 = pv + fmaf(pv, ds, r1);
-                        if (noisy) res1 = fmaf(scale, nzv[1], res1);
-                        out[1] = res1;
+#pragma unroll
+                    for (int j = 0; j < G::NV; ++j) {
+                        float res = pv + fmaf(pv, ds, v[j]);
+                        if (noisy) res = fmaf(scale, nzv[j], res);
+                        out[j] = res;
                     }
                 }
             }
@@ -429,9 +432,11 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
     }
 }
 
-template <int K, int S>
-int launch_kS(const CUtensorMap& tmap, StreamArgs& t, int sms, cudaStream_t st) {
-    using G = Cfg<K, S>;
+template <int K, int S, int TX>
+int launch_kS(const DegradeArgs& a, StreamArgs& t, int sms, cudaStream_t st) {
+    using G = Cfg<K, S, TX>;
+    t.nw = t.BW / (32 * TX) > 0 ? t.BW / (32 * TX) : 1;
+    t.ns = kConsumers / t.nw;
     // row pitch: AL | BW | right extent of the last group, 16-byte granules, odd count
     const int right = G::LOADF - G::GW - G::AL;
     int pitch = G::AL + t.BW + (right > 0 ? right : 0);
@@ -466,7 +471,20 @@ int launch_kS(const CUtensorMap& tmap, StreamArgs& t, int sms, cudaStream_t st) 
     t.barOff = (unsigned)ring;
     t.wOff = (unsigned)(ring + ((2 * t.ns * depth * 8 + 127) / 128) * 128);
     const size_t smem = t.wOff + wbytes;
-    auto kern = degrade_stream_kernel<K, S>;
+    KMSR_REQUIRE(pitch / 2 <= 256, KMSR_E_UNSUPPORTED, "degrade (stream): staged row of %d floats exceeds the TMA box limit", pitch);
+    EncodeTiledFn enc = get_tensor_map_encoder();
+    KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "degrade (stream): cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap tmap;
+    cuuint64_t gdim[4] = {(cuuint64_t)(a.W / 2), (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.N};
+    const long long sN = a.N > 1 ? a.sN : (long long)a.C * a.sC;
+    cuuint64_t gstr[3] = {(cuuint64_t)a.sH * 4, (cuuint64_t)a.sC * 4, (cuuint64_t)sN * 4};
+    cuuint32_t box[4] = {(cuuint32_t)(pitch / 2), (cuuint32_t)S, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)a.hr, gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "degrade (stream): cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    auto kern = degrade_stream_kernel<K, S, TX>;
     KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (t.nitems + t.ns - 1) / t.ns;
     if (grid > sms) grid = sms;
@@ -476,11 +494,15 @@ int launch_kS(const CUtensorMap& tmap, StreamArgs& t, int sms, cudaStream_t st) 
 }
 
 template <int K>
-int launch_k(const CUtensorMap& tmap, StreamArgs& t, int S, int sms, cudaStream_t st) {
+int launch_k(const DegradeArgs& a, StreamArgs& t, int S, int sms, cudaStream_t st) {
     switch (S) {
-        case 2: return launch_kS<K, 2>(tmap, t, sms, st);
-        case 4: return launch_kS<K, 4>(tmap, t, sms, st);
-        default: return launch_kS<K, 8>(tmap, t, sms, st);
+        case 2: return launch_kS<K, 2, 4>(a, t, sms, st);
+        case 4:
+            // 8 LR columns per lane when the accumulator sets still fit (Q <= 4, i.e. k <= 13: +6..16 %; k = 15
+            // spills and loses 20 %, r52)
+            if constexpr (kWide4 && (K + 3 + 3) / 4 <= 4) { if (t.BW == 256) return launch_kS<K, 4, 8>(a, t, sms, st); }
+            return launch_kS<K, 4, 4>(a, t, sms, st);
+        default: return launch_kS<K, 8, 4>(a, t, sms, st);     // 8 columns per lane at factor 8: 8 streams no longer fit, spills
     }
 }
 
@@ -508,8 +530,6 @@ bool stream_shape_ok(const DegradeArgs& a, int down_mode, const char** why) {
 }
 
 int launch_degrade_stream(const DegradeArgs& a, cudaStream_t st) {
-    EncodeTiledFn enc = get_tensor_map_encoder();
-    KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "degrade (stream): cuTensorMapEncodeTiled is not available from the driver");
     const Geometry& g = a.g;
     const int S = g.stride, K = g.kh;
     StreamArgs t;
@@ -518,43 +538,20 @@ int launch_degrade_stream(const DegradeArgs& a, cudaStream_t st) {
     t.C = a.C; t.H = a.H; t.W = a.W; t.Ho = g.Ho; t.Wo = g.Wo;
     t.BW = a.W >= 256 ? 256 : a.W;
     t.nblk = a.W / t.BW;
-    t.nw = t.BW == 256 ? 2 : 1;
-    t.ns = kConsumers / t.nw;
+    t.nw = 1; t.ns = kConsumers;             // set per <K, S, TX> in launch_kS
     t.nitems = a.N * a.C * t.nblk;
     t.pad_mode = a.pad_mode; t.noise_mode = a.noise_mode;
-
-    // staged row: pitch floats starting AL columns left of the block; pitch is fixed by <K, S> and BW
-    int AL = (K / 2 + 3) / 4 * 4;
-    const int KW = K + S - 1;
-    const int SEG = KW + 3 * S, SKEW = AL - K / 2;
-    const int LOADF = (SKEW + SEG + 3) / 4 * 4;
-    const int right = LOADF - 4 * S - AL;
-    int pitch = AL + t.BW + (right > 0 ? right : 0);
-    pitch = (pitch + 3) / 4 * 4;
-    if ((pitch / 4) % 2 == 0) pitch += 4;
-    KMSR_REQUIRE(pitch / 2 <= 256, KMSR_E_UNSUPPORTED, "degrade (stream): staged row of %d floats exceeds the TMA box limit", pitch);
-
-    CUtensorMap tmap;
-    cuuint64_t gdim[4] = {(cuuint64_t)(a.W / 2), (cuuint64_t)a.H, (cuuint64_t)a.C, (cuuint64_t)a.N};
-    const long long sN = a.N > 1 ? a.sN : (long long)a.C * a.sC;
-    cuuint64_t gstr[3] = {(cuuint64_t)a.sH * 4, (cuuint64_t)a.sC * 4, (cuuint64_t)sN * 4};
-    cuuint32_t box[4] = {(cuuint32_t)(pitch / 2), (cuuint32_t)S, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)a.hr, gdim, gstr, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "degrade (stream): cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
 
     int dev = 0, sms = 0;
     KMSR_CUDA_OK(cudaGetDevice(&dev));
     KMSR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     set_algo("stream");
     switch (K) {
-        case 11: return launch_k<11>(tmap, t, S, sms, st);
-        case 13: return launch_k<13>(tmap, t, S, sms, st);
-        case 15: return launch_k<15>(tmap, t, S, sms, st);
-        case 21: return launch_k<21>(tmap, t, S, sms, st);
-        default: return launch_k<31>(tmap, t, S, sms, st);
+        case 11: return launch_k<11>(a, t, S, sms, st);
+        case 13: return launch_k<13>(a, t, S, sms, st);
+        case 15: return launch_k<15>(a, t, S, sms, st);
+        case 21: return launch_k<21>(a, t, S, sms, st);
+        default: return launch_k<31>(a, t, S, sms, st);
     }
 }
 
