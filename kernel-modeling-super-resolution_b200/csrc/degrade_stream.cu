@@ -495,6 +495,14 @@ int launch_kS(const DegradeArgs& a, StreamArgs& t, int sms, cudaStream_t st) {
 
 template <int K>
 int launch_k(const DegradeArgs& a, StreamArgs& t, int S, int sms, cudaStream_t st) {
+    // 64-wide patches: two LR columns per lane keep all 32 lanes of the (single) warp of a stream busy
+    if (t.BW == 64) {
+        switch (S) {
+            case 2: return launch_kS<K, 2, 2>(a, t, sms, st);
+            case 4: return launch_kS<K, 4, 2>(a, t, sms, st);
+            default: return launch_kS<K, 8, 2>(a, t, sms, st);
+        }
+    }
     switch (S) {
         case 2: return launch_kS<K, 2, 4>(a, t, sms, st);
         case 4:
