@@ -220,6 +220,24 @@ KMSR_API int kmsr_scene_keep_mask(const float* data, int C, int H, int W, int ni
                                   uint8_t* keep, int32_t* nan_count,
                                   void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- f4: upstream denoise stage (denoise/denoise.py:34-65 denoise_band_float_nlm) -----------------
+ * Produces the `denoised` group that D_build_noise_pool.py:85 and E_make_train_data.py:234 read.  Per band:
+ * NaN pixels are filled with the band's nanmean (:43-44), sigma = skimage estimate_sigma (:47: MAD of the db2
+ * 'dd' coefficients of pywt.dwtn / 0.6745), out = skimage denoise_nl_means(fast_mode=True, patch_size,
+ * patch_distance, h = h_factor * sigma, sigma = sigma) (:56-63), NaN pixels restored (:66).  An all-NaN band
+ * is returned unchanged with sigma 0.0 (:40-41).  skimage / PyWavelets are third-party and absent from the
+ * build image: their published algorithms are restated ("parity unpinned").
+ *   x, out [N, C, H, W] float32 (patch stride x_stride_n elements; out contiguous, must not alias x)
+ *   sigma  [N, C] float64  (what the reference returns next to the band and stores as `<band>_sigma`, :248)
+ *   patch_size 7 (6 is rounded up to 7 as skimage does), patch_distance 0..11: KMSR_E_UNSUPPORTED otherwise
+ *   workspace: kmsr_denoise_workspace_bytes(N, C, H, W), 256-byte aligned                                */
+KMSR_API int64_t kmsr_denoise_workspace_bytes(int64_t N, int C, int H, int W);
+KMSR_API int kmsr_estimate_sigma(const float* x, int64_t N, int C, int H, int W, int64_t x_stride_n,
+                                 double* sigma, void* workspace, int64_t workspace_bytes, void* stream);
+KMSR_API int kmsr_denoise_nlm(const float* x, int64_t N, int C, int H, int W, int64_t x_stride_n,
+                              double h_factor, int patch_size, int patch_distance, float* out, double* sigma,
+                              void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------
  * Launch counter: number of kernels this library launched on the calling process since load.   */
 KMSR_API int64_t kmsr_launch_count(void);

@@ -34,6 +34,11 @@ int launch_scene_keep_mask(const float*, int, int, int, int, float, float, float
                            int*, void*, long long, cudaStream_t);
 int launch_keep_mask(const float*, int, int, int, int, int, double, unsigned char*, int*, void*,
                      long long, cudaStream_t);
+long long denoise_workspace(long long, int, int, int);
+int launch_estimate_sigma(const float*, long long, int, int, int, long long, double*, void*, long long, cudaStream_t);
+int launch_nlm(const float*, long long, int, int, int, long long, const double*, const double*, double, int, float*,
+               cudaStream_t);
+bool nlm_shape_ok(int, int, const char**);
 
 }  // namespace kmsr
 
@@ -302,6 +307,44 @@ KMSR_API int kmsr_keep_mask(const float* masked, int C, int H, int W, int P, int
     KMSR_REQUIRE(masked && keep, KMSR_E_INVALID, "keep_mask: null pointer");
     return launch_keep_mask(masked, C, H, W, P, stride, nan_threshold, keep, nan_count, workspace,
                             workspace_bytes, (cudaStream_t)stream);
+}
+
+KMSR_API int64_t kmsr_denoise_workspace_bytes(int64_t N, int C, int H, int W) {
+    if (N < 0 || C < 1 || H < 2 || W < 2) {
+        set_error("denoise_workspace_bytes: N=%lld C=%d H=%d W=%d", (long long)N, C, H, W);
+        return KMSR_E_INVALID;
+    }
+    return denoise_workspace(N, C, H, W);
+}
+
+KMSR_API int kmsr_estimate_sigma(const float* x, int64_t N, int C, int H, int W, int64_t x_stride_n, double* sigma,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+    KMSR_REQUIRE(N >= 0 && C >= 1 && H >= 2 && W >= 2, KMSR_E_INVALID, "estimate_sigma: N=%lld C=%d H=%d W=%d",
+                 (long long)N, C, H, W);
+    if (N == 0) return KMSR_OK;
+    KMSR_REQUIRE(x && sigma && workspace, KMSR_E_INVALID, "estimate_sigma: null pointer");
+    KMSR_REQUIRE(x_stride_n >= (int64_t)C * H * W, KMSR_E_INVALID, "estimate_sigma: patch stride %lld < C*H*W",
+                 (long long)x_stride_n);
+    return launch_estimate_sigma(x, N, C, H, W, x_stride_n, sigma, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+KMSR_API int kmsr_denoise_nlm(const float* x, int64_t N, int C, int H, int W, int64_t x_stride_n, double h_factor,
+                              int patch_size, int patch_distance, float* out, double* sigma, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+    KMSR_REQUIRE(N >= 0 && C >= 1 && H >= 2 && W >= 2, KMSR_E_INVALID, "denoise_nlm: N=%lld C=%d H=%d W=%d", (long long)N,
+                 C, H, W);
+    const char* why = "";
+    KMSR_REQUIRE(nlm_shape_ok(patch_size, patch_distance, &why), KMSR_E_UNSUPPORTED,
+                 "denoise_nlm: patch_size=%d patch_distance=%d not covered: %s", patch_size, patch_distance, why);
+    if (N == 0) return KMSR_OK;
+    KMSR_REQUIRE(x && out && sigma && workspace, KMSR_E_INVALID, "denoise_nlm: null pointer");
+    KMSR_REQUIRE(x != out, KMSR_E_INVALID, "denoise_nlm: out must not alias x (every tile reads its neighbours' pixels)");
+    KMSR_REQUIRE(x_stride_n >= (int64_t)C * H * W, KMSR_E_INVALID, "denoise_nlm: patch stride %lld < C*H*W",
+                 (long long)x_stride_n);
+    int rc = launch_estimate_sigma(x, N, C, H, W, x_stride_n, sigma, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (rc != KMSR_OK) return rc;
+    return launch_nlm(x, N, C, H, W, x_stride_n, reinterpret_cast<const double*>(workspace), sigma, h_factor, patch_distance,
+                      out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -312,3 +312,47 @@ def scene_keep_mask(scene: torch.Tensor, tmin: float, tmax: float, patch_size: i
                                                  patch_size, stride, float(nan_threshold), _ptr(keep), _ptr(cnt), _ptr(ws),
                                                  wsb, _stream(dev)))
     return keep.bool(), cnt
+
+
+def _bands_nchw(x: torch.Tensor):
+    if x.ndim != 4:
+        raise ValueError(f"expected [N,C,H,W], got {tuple(x.shape)}")
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise TypeError("expected a CUDA float32 tensor (drop-in wrappers copy host inputs)")
+    N, Cc, H, W = x.shape
+    if x.stride(3) != 1 or x.stride(2) != W or x.stride(1) != H * W:
+        x = x.contiguous()
+    return x, N, Cc, H, W, (x.stride(0) if N > 1 else Cc * H * W)
+
+
+def estimate_sigma(x: torch.Tensor) -> torch.Tensor:
+    """skimage.restoration.estimate_sigma of every band (denoise/denoise.py:47) -> [N,C] float64 on the device.
+    NaN pixels are read as the band's nanmean (denoise.py:43-44); an all-NaN band reports 0.0 (:40-41)."""
+    require_cuda()
+    x, N, Cc, H, W, sn = _bands_nchw(x)
+    dev = x.device
+    sigma = torch.empty((N, Cc), dtype=torch.float64, device=dev)
+    wsb = L.check(int(L.lib().kmsr_denoise_workspace_bytes(N, Cc, H, W)))
+    ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().kmsr_estimate_sigma(_ptr(x), N, Cc, H, W, sn, _ptr(sigma), _ptr(ws), wsb, _stream(dev)))
+    return sigma
+
+
+def denoise_nlm(x: torch.Tensor, h_factor: float = 1.15, patch_size: int = 7, patch_distance: int = 11,
+                out: torch.Tensor | None = None):
+    """denoise_band_float_nlm (denoise/denoise.py:34-65) of every band of x [N,C,H,W] -> (denoised [N,C,H,W] f32,
+    sigma [N,C] f64): nanmean fill, estimate_sigma, fast-mode non-local means with h = h_factor * sigma, NaN restore."""
+    require_cuda()
+    x, N, Cc, H, W, sn = _bands_nchw(x)
+    dev = x.device
+    if out is None:
+        out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=dev)
+    assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (N, Cc, H, W)
+    sigma = torch.empty((N, Cc), dtype=torch.float64, device=dev)
+    wsb = L.check(int(L.lib().kmsr_denoise_workspace_bytes(N, Cc, H, W)))
+    ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().kmsr_denoise_nlm(_ptr(x), N, Cc, H, W, sn, float(h_factor), int(patch_size), int(patch_distance),
+                                         _ptr(out), _ptr(sigma), _ptr(ws), wsb, _stream(dev)))
+    return out, sigma

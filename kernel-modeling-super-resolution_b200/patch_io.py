@@ -119,9 +119,11 @@ def write_groups(path: str, groups: dict, attrs: dict | None = None) -> None:
 
 
 def add_group(path: str, group: str, bands: np.ndarray, band_names=BAND_NAMES, dims=("y", "x"),
-              history: str | None = None, long_name: str | None = None, src: str | None = None) -> None:
+              history: str | None = None, long_name: str | None = None, src: str | None = None,
+              group_attrs: dict | None = None) -> None:
     """Write `bands` [C,h,w] as group `group` of `path`; with `src` the file is first copied from it
-    (C_30:171: shutil.copy then open in append mode); existing variables are overwritten (C_31:170-173)."""
+    (C_30:171: shutil.copy then open in append mode); existing variables are overwritten (C_31:170-173).
+    `group_attrs` become attributes of the group (denoise/denoise.py:236-252)."""
     if src is not None:
         shutil.copy(src, path)
     if path.endswith(".npz"):
@@ -130,6 +132,8 @@ def add_group(path: str, group: str, bands: np.ndarray, band_names=BAND_NAMES, d
             z[f"{group}/{b}"] = np.asarray(bands[c], dtype=np.float32)
         if history is not None:
             z["__attrs__/history"] = np.array(history)
+        for k, v in (group_attrs or {}).items():
+            z[f"__attrs__/{group}/{k}"] = np.array(v)
         np.savez_compressed(path, **z)
         return
     with _nc().Dataset(path, "a", format="NETCDF4") as ds:
@@ -143,6 +147,8 @@ def add_group(path: str, group: str, bands: np.ndarray, band_names=BAND_NAMES, d
             if long_name:
                 var.long_name = long_name.format(wl=b.split("_")[-1])
             var.units = "W m-2 sr-1 um-1"
+        for k, v in (group_attrs or {}).items():
+            setattr(grp, k, v)
         if history is not None:
             ds.history = history
 

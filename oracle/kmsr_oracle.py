@@ -294,3 +294,28 @@ def band_range(hr: np.ndarray) -> np.ndarray:
 def rel_err(a: np.ndarray, b: np.ndarray, rng: np.ndarray) -> float:
     """max |a-b| / per-band range."""
     return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)) / rng))
+
+
+# --------------------------------------------------------------------------
+# f4  denoise_band_float_nlm  (denoise/denoise.py:34-68) -- PARITY UNPINNED
+# --------------------------------------------------------------------------
+# skimage.restoration.{estimate_sigma, denoise_nl_means} and PyWavelets are absent from this image, so this
+# call-site port cannot issue the reference's library calls; it strings the reference's own numpy lines around
+# the restated algorithms of oracle/oracle_nlm.c (see its header for what is restated and why it is unpinned).
+def denoise_band_float_nlm(img_float, h_factor=1.15, patch_size=7, patch_distance=11, exact=False, eps=0.0):
+    """Returns (denoised, sigma) like denoise.py:34-68; with exact=True the fp64 evaluation and the per-pixel
+    cut-off sensitivity `flip` are returned as (denoised64, sigma, flip)."""
+    from oracle import oracle_c
+    img_float = np.asarray(img_float)
+    valid_mask = ~np.isnan(img_float)                                             # :38
+    if not valid_mask.any():                                                       # :39-40
+        return (img_float, 0.0, None) if exact else (img_float, 0.0)
+    fill_value = np.nanmean(img_float)                                             # :42
+    img_filled = np.nan_to_num(img_float, nan=fill_value).astype(np.float32)       # :43
+    estimated_sigma = oracle_c.estimate_sigma(img_filled)                          # :46
+    h_val = h_factor * estimated_sigma                                             # :49
+    if exact:
+        den, flip = oracle_c.nlm_exact_f64(img_filled, h_val, estimated_sigma, patch_size, patch_distance, eps)
+        return np.where(valid_mask, den, np.nan), estimated_sigma, flip
+    den = oracle_c.nlm_fast_f32(img_filled, h_val, estimated_sigma, patch_size, patch_distance)   # :55-62
+    return np.where(valid_mask, den, np.nan), estimated_sigma                      # :65

@@ -12,8 +12,8 @@ _SO = os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "oracle.c")
-    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle_nlm.c")]
+    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
     return _SO
 
@@ -123,3 +123,44 @@ def keep_mask(masked, patch=256, stride=128, nan_thr=0.0):
     if hp > 0 and wp > 0:
         lib().orc_keep_mask(_p(masked, C.c_float), c, h, w, patch, stride, C.c_double(nan_thr), _p(keep, C.c_uint8), hp, wp)
     return keep.astype(bool)
+
+
+# ---- f4: upstream denoise stage (denoise/denoise.py:34-65), oracle_nlm.c -- PARITY UNPINNED (see its header)
+def estimate_sigma(img: np.ndarray, return_dd: bool = False, f64: bool = False):
+    """skimage.restoration.estimate_sigma of one 2-D float32 image (db2 'dd' coefficients, MAD / 0.6745).
+    f64=True evaluates the transform in float64 (the value the float32 transform approximates)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    h, w = img.shape
+    if f64:
+        fn = lib().orc_estimate_sigma_f64
+        fn.restype = C.c_double
+        return float(fn(_p(img, C.c_float), h, w))
+    dd = np.empty(((h + 3) // 2, (w + 3) // 2), dtype=np.float32) if return_dd else None
+    fn = lib().orc_estimate_sigma
+    fn.restype = C.c_double
+    s = fn(_p(img, C.c_float), h, w, None if dd is None else _p(dd, C.c_float))
+    return (float(s), dd) if return_dd else float(s)
+
+
+def nlm_fast_f32(img: np.ndarray, h: float, sigma: float, patch_size: int = 7, patch_distance: int = 11) -> np.ndarray:
+    """skimage denoise_nl_means(fast_mode=True) of one float32 band, integral-image algorithm in float32."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    out = np.empty_like(img)
+    rc = lib().orc_nlm_fast_f32(_p(img, C.c_float), img.shape[0], img.shape[1], patch_size, patch_distance,
+                                C.c_float(np.float32(h)), C.c_float(np.float32(sigma * sigma)), _p(out, C.c_float))
+    assert rc == 0
+    return out
+
+
+def nlm_exact_f64(img: np.ndarray, h: float, sigma: float, patch_size: int = 7, patch_distance: int = 11,
+                  eps: float = 0.0):
+    """The same formula in float64.  Returns (out, flip): flip bounds what the distance cut-off can change per pixel
+    when a distance moves by less than eps (None when eps == 0)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    out = np.empty(img.shape, dtype=np.float64)
+    flip = np.empty(img.shape, dtype=np.float64) if eps > 0 else None
+    rc = lib().orc_nlm_exact_f64(_p(img, C.c_float), img.shape[0], img.shape[1], patch_size, patch_distance,
+                                 C.c_float(np.float32(h)), C.c_float(np.float32(sigma * sigma)), C.c_double(eps),
+                                 _p(out, C.c_double), None if flip is None else _p(flip, C.c_double))
+    assert rc == 0
+    return out, flip
