@@ -39,5 +39,11 @@ ops.keep_mask(m, 256, 128, 0.0)
 ops.band_stats(hr)
 ops.add_noise_batch(torch.zeros(n, 5, 32, 32, device="cuda"), pool, nidx)
 ops.crop_sub(dev_scene, m, np.array([0, 600], dtype=np.int32), np.array([0, 860], dtype=np.int32), 32)
+xd = hr[:2, :, :72, :100].clone()
+xd[0, 1, 3:9, 4:20] = float("nan")
+xd[1, 4] = float("nan")
+ops.denoise_nlm(xd, 1.8)
+ops.estimate_sigma(xd)
+print("denoise")
 torch.cuda.synchronize()
 print("done")
