@@ -12,13 +12,13 @@ LIB_PATH = os.path.join(_HERE, "libkmsr.so")
 PAD_REPLICATE, PAD_ZERO = 0, 1
 DOWN_BOXMEAN, DOWN_DECIMATE = 0, 1
 NOISE_NONE, NOISE_ADD, NOISE_SIGMA = 0, 1, 2
-ALGO_AUTO, ALGO_TILED, ALGO_TMA, ALGO_STREAM = 0, 1, 2, 3
+ALGO_AUTO, ALGO_TILED, ALGO_TMA, ALGO_STREAM, ALGO_REG = 0, 1, 2, 3, 4
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_ALIGN = -1, -2, -3, -4
 
 PAD_MODES = {"replicate": PAD_REPLICATE, "zero": PAD_ZERO}
 DOWN_MODES = {"boxmean": DOWN_BOXMEAN, "decimate": DOWN_DECIMATE}
 NOISE_MODES = {"none": NOISE_NONE, "add": NOISE_ADD, "sigma": NOISE_SIGMA}
-ALGOS = {"auto": ALGO_AUTO, "tiled": ALGO_TILED, "tma": ALGO_TMA, "stream": ALGO_STREAM}
+ALGOS = {"auto": ALGO_AUTO, "tiled": ALGO_TILED, "tma": ALGO_TMA, "stream": ALGO_STREAM, "reg": ALGO_REG}
 
 
 class KmsrError(RuntimeError):

@@ -119,7 +119,7 @@ static int degrade_common(const float* hr, int64_t N, int C, int H, int W, int64
                  "degrade: pad_mode %d", pad_mode);
     KMSR_REQUIRE(noise_mode >= KMSR_NOISE_NONE && noise_mode <= KMSR_NOISE_SIGMA, KMSR_E_INVALID,
                  "degrade: noise_mode %d", noise_mode);
-    KMSR_REQUIRE(algo >= KMSR_ALGO_AUTO && algo <= KMSR_ALGO_STREAM, KMSR_E_INVALID, "degrade: algo %d", algo);
+    KMSR_REQUIRE(algo >= KMSR_ALGO_AUTO && algo <= KMSR_ALGO_REG, KMSR_E_INVALID, "degrade: algo %d", algo);
     if (N == 0 || a.g.Ho == 0 || a.g.Wo == 0) return KMSR_OK;
     KMSR_REQUIRE(H >= 1 && W >= 1, KMSR_E_INVALID, "degrade: empty patch %dx%d", H, W);
     KMSR_REQUIRE(hr && comp && dsum && lr, KMSR_E_INVALID, "degrade: null pointer");
@@ -145,6 +145,14 @@ static int degrade_common(const float* hr, int64_t N, int C, int H, int W, int64
         return launch_degrade_tma(a, st);
     }
     if (algo == KMSR_ALGO_AUTO && tma_ok) return launch_degrade_tma(a, st);
+    const char* why3 = "";
+    const bool reg_ok = stat_part == nullptr && reg_shape_ok(a, down_mode, &why3);
+    if (algo == KMSR_ALGO_REG) {
+        KMSR_REQUIRE(reg_ok, KMSR_E_UNSUPPORTED, "degrade: register-tile kernel does not cover this call (%s)", why3);
+        return launch_degrade_reg(a, st);
+    }
+    // FP32-bound shapes: factor 2 (1.3-2.2x over the streaming kernel on every sweep cell), factor 4 on 64-wide patches
+    if (algo == KMSR_ALGO_AUTO && reg_ok && (a.g.stride == 2 || a.W <= 64)) return launch_degrade_reg(a, st);
     const char* why2 = "";
     const bool stream_ok = stat_part == nullptr && stream_shape_ok(a, down_mode, &why2);
     if (algo == KMSR_ALGO_STREAM) {
@@ -152,6 +160,7 @@ static int degrade_common(const float* hr, int64_t N, int C, int H, int W, int64
         return launch_degrade_stream(a, st);
     }
     if (algo == KMSR_ALGO_AUTO && stream_ok) return launch_degrade_stream(a, st);
+    if (algo == KMSR_ALGO_AUTO && reg_ok) return launch_degrade_reg(a, st);      // factor-4 shapes the streaming kernel refuses
     return launch_degrade_tiled(a, st);
 }
 

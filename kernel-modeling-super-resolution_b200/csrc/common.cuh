@@ -110,5 +110,7 @@ bool tma_shape_ok(const DegradeArgs& a, const char** why);
 int launch_degrade_tma(const DegradeArgs& a, cudaStream_t st);
 bool stream_shape_ok(const DegradeArgs& a, int down_mode, const char** why);
 int launch_degrade_stream(const DegradeArgs& a, cudaStream_t st);
+bool reg_shape_ok(const DegradeArgs& a, int down_mode, const char** why);
+int launch_degrade_reg(const DegradeArgs& a, cudaStream_t st);
 
 }  // namespace kmsr

@@ -340,6 +340,49 @@ def test_generic_streaming_kernel(K, synth, k, s, p):
         assert np.array_equal(np.isnan(ln[i]), np.isnan(ref)), (k, s, p, i)
 
 
+@pytest.mark.parametrize("k,s,h,w", [(11, 2, 64, 64), (13, 2, 128, 128), (15, 4, 256, 256), (21, 2, 256, 256), (31, 4, 128, 128),
+                                     (31, 2, 64, 64), (21, 4, 512, 512), (11, 4, 64, 64), (13, 2, 72, 200), (15, 2, 130, 66),
+                                     (31, 2, 40, 300), (13, 4, 100, 36)])
+def test_register_tile_kernel(K, synth, k, s, h, w):
+    """degrade_reg<K, S> (the FP32-bound shapes of BASELINE config 5; any H / W, partial tiles, narrow groups):
+    replicate and zero padding, noise epilogue, NaN footprint, strided views, against the reference call sites."""
+    n = 3
+    kern = synth.softmax_kernels(k, 7 + k)
+    p = max(h, w)
+    p = (p + 63) // 64 * 64
+    full = np.concatenate([synth.make_hr(2, 3000 + k + s, "textured", size=p), synth.make_hr(1, 3100 + k, "water", size=p)])
+    hr = np.ascontiguousarray(full[:, :, :h, :w])
+    hd = torch.from_numpy(full).cuda()[:, :, :h, :w]           # a strided view: rows contiguous, row stride p
+    kd = torch.from_numpy(kern).cuda()
+    lr = K.ops.degrade_batch(hd, kd, factor=s, algo="reg").cpu().numpy()
+    assert K.lib.last_algo() == "reg" and lr.shape == (n, 5, h // s, w // s)
+    for i in range(n):
+        ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kern), s).numpy()
+        check_pixels(lr[i], ref, hr[i], exact_degrade(hr[i], kern, s), name=f"reg k{k} s{s} {h}x{w} #{i}")
+    # zero padding (train_gemini.py:128) + sigma noise: held to the exact (fp64) value
+    ho, wo = h // s, w // s
+    pool = (np.random.RandomState(3).standard_normal((5, 5, ho, wo)) * 0.5).astype(np.float32)
+    sig = np.linspace(0.7, 1.0, 5, dtype=np.float32)[None]
+    nidx = np.array([4, 0, 2], dtype=np.int32)
+    lz = K.ops.degrade_batch(hd, kd, factor=s, pad_mode="zero", sigma=torch.from_numpy(sig), pool=torch.from_numpy(pool).cuda(),
+                             nidx=nidx, noise_mode="sigma", algo="reg").cpu().numpy()
+    for i in range(n):
+        rngs = orc.band_range(hr[i])
+        ex = exact_degrade(hr[i], kern, s, zero_pad=True) + sig[0][:, None, None].astype(np.float64) * pool[nidx[i]]
+        slack = np.spacing(np.abs(ex).astype(np.float32)).astype(np.float64) / rngs
+        tol = 5e-6 if i < 2 else 5e-6 * float(np.abs(hr[i]).max()) / float(rngs.min())
+        assert (np.abs(lz[i] - ex) / rngs <= tol + slack).all(), (k, s, h, w, i, float((np.abs(lz[i] - ex) / rngs).max()))
+    # NaN footprint
+    hn = hr.copy()
+    hn[0, 1, 0, 0] = np.nan
+    hn[1, 3, h // 2, w // 3] = np.nan
+    hn[2, 0, h - 1, w - 1] = np.nan
+    ln = K.ops.degrade_batch(torch.from_numpy(hn).cuda(), kd, factor=s, algo="reg").cpu().numpy()
+    for i in range(n):
+        ref = orc.apply_kernel_degradation(torch.from_numpy(hn[i]), torch.from_numpy(kern), s).numpy()
+        assert np.array_equal(np.isnan(ln[i]), np.isnan(ref)), (k, s, h, w, i)
+
+
 def test_nan_propagation_matches_reference(K, synth, bank):
     """A NaN pixel poisons exactly the LR pixels whose (clamped) window contains it."""
     kb, _ = bank
@@ -593,6 +636,16 @@ def test_shapes_the_streaming_kernels_hand_to_each_other(K, synth, bank):
     assert K.lib.last_algo() == "tiled"
     K.ops.degrade_batch(hr[:, :, :128, :128].contiguous(), kd, factor=4)
     assert K.lib.last_algo() == "stream"
+    # FP32-bound shapes go to the register-tile kernel: factor 2, factor 4 on 64-wide patches, and the factor-4
+    # shapes the streaming kernel refuses (widths that are not 64 / 128 / 256 m)
+    r2 = K.ops.degrade_batch(hr, kd, factor=2)
+    assert K.lib.last_algo() == "reg"
+    s2 = K.ops.degrade_batch(hr, kd, factor=2, algo="stream")
+    assert K.lib.last_algo() == "stream" and float(((r2 - s2).abs() / rngs).max()) <= 2e-6
+    K.ops.degrade_batch(hr[:, :, :64, :64].contiguous(), kd, factor=4)
+    assert K.lib.last_algo() == "reg"
+    K.ops.degrade_batch(hr[:, :, :100, :36].contiguous(), kd, factor=4)
+    assert K.lib.last_algo() == "reg"
     # strided views: a channel slice of a wider tensor still streams (16-byte aligned strides)
     wide = torch.randn(4, 7, 256, 256, device="cuda") + 30.0
     v = wide[:, 1:6]
