@@ -19,6 +19,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -62,25 +63,83 @@ def ncu_traffic():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  The timed region of the
+    default run lasts ~20 ms, shorter than one `nvidia-smi -lms` period, so the samples come from NVML directly
+    (pynvml, a polling thread, ~1 ms period); `nvidia-smi -lms 100` is the fallback when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.f = None
+        self.thread = None
+        self.samples = []
+        self.stop_flag = False
+        self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.idx)
+        while not self.stop_flag:
+            try:
+                clk = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((clk, rs, pw))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.idx = self._nvml_index()
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def _nvml_index(self) -> int:
+        # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists plain indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip().isdigit()]
+        return int(ids[self.idx]) if self.idx < len(ids) else self.idx
+
     def stop(self) -> dict:
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            n = self.nvml
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            sm = sorted(float(c) for c, _, _ in self.samples)
+            bits = 0
+            for _, r, _ in self.samples:
+                bits |= int(r)
+            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                    getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                    getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+            reasons = sorted(k for k, v in names.items() if bits & int(v))
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "power_w_max": max(p for _, _, p in self.samples), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -99,7 +158,7 @@ class ClockSampler:
         reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.strip().lower().startswith("active")})
         pw = max(float(r[3]) for r in rows)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
-                "samples": len(rows), "power_w_max": pw}
+                "samples": len(rows), "power_w_max": pw, "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
