@@ -39,6 +39,11 @@ ops.keep_mask(m, 256, 128, 0.0)
 ops.band_stats(hr)
 ops.add_noise_batch(torch.zeros(n, 5, 32, 32, device="cuda"), pool, nidx)
 ops.crop_sub(dev_scene, m, np.array([0, 600], dtype=np.int32), np.array([0, 860], dtype=np.int32), 32)
+for k, h, w, s in ((11, 64, 64, 2), (31, 72, 200, 2), (13, 100, 36, 4), (21, 256, 256, 2)):
+    x = torch.from_numpy(synth.make_hr(3, 2, "textured", size=256)).cuda()[:, :, :h, :w]
+    for pad in ("replicate", "zero"):
+        ops.degrade_batch(x, torch.from_numpy(synth.softmax_kernels(k, 7)).cuda(), factor=s, pad_mode=pad, algo="reg")
+    print("reg", k, h, w, s)
 xd = hr[:2, :, :72, :100].clone()
 xd[0, 1, 3:9, 4:20] = float("nan")
 xd[1, 4] = float("nan")
