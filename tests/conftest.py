@@ -1,4 +1,3 @@
-import importlib.util
 import os
 import sys
 

@@ -9,7 +9,6 @@ import hashlib
 import os
 import random
 import re
-import tempfile
 
 import numpy as np
 import pytest
