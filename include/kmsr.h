@@ -64,8 +64,8 @@ enum {
 enum {
     KMSR_ALGO_AUTO = 0,    /* headline TMA kernel, else the generic streaming kernel, else the tiled kernel */
     KMSR_ALGO_TILED = 1,   /* polyphase shared-memory tile kernel (any k, factor, H, W, pad / down mode)   */
-    KMSR_ALGO_TMA = 2,     /* headline TMA row-streaming kernel (k = 13, factor 8, W = 256); KMSR_E_UNSUPPORTED
-                              if the shape does not qualify                                                */
+    KMSR_ALGO_TMA = 2,     /* headline TMA row-streaming kernel (k = 13, factor 8, W a multiple of 256, H % 8 == 0,
+                              H <= 512); KMSR_E_UNSUPPORTED if the shape does not qualify                      */
     KMSR_ALGO_STREAM = 3,  /* generic TMA row-streaming kernel (k in 11/13/15/21/31, factor 2/4/8, box mean,
                               W in 64/128/256*m); KMSR_E_UNSUPPORTED otherwise                             */
     KMSR_ALGO_REG = 4      /* register-tile stencil kernel for the FP32-bound shapes (k in 11/13/15/21/31,

@@ -1,5 +1,5 @@
 // degrade_tma.cu -- TMA row-streaming fused blur + downsample + noise kernel for the headline shape
-// (k = 13, factor 8, replicate padding, W = 256, H a multiple of 8; BASELINE configs 1-3).
+// (k = 13, factor 8, replicate padding, W = 256 or a multiple of it, H a multiple of 8; BASELINE configs 1-3).
 //
 // Same arithmetic as degrade_tiled.cu (C_30apply_kernel_to_landsat.py:68-124 with the box mean
 // folded into a 20 x 20 stride-8 composite kernel, E_make_train_data.py:72-74 /
@@ -61,7 +61,7 @@ constexpr int kSkew = kLeftF - kPad;           // 2: the segment starts 2 floats
 constexpr int kLoadF = (kSkew + kSegF + 3) / 4 * 4;   // 48 floats = 12 LDS.128
 constexpr size_t kBarOff = (size_t)kStreams * kDepth * kChunkBytes;                 // full/empty mbarriers
 constexpr size_t kStageOff = kBarOff + ((2 * kStreams * kDepth * 8 + 127) / 128) * 128;   // per-warp weight staging
-constexpr int kMaxHo = 32;                     // noise staging covers H <= 256
+constexpr int kMaxHo = 64;                     // noise staging covers H <= 512
 constexpr int kNoiseF = kMaxHo * 16;           // a warp's 16 output columns x Ho rows
 constexpr size_t kStageBytes = ((size_t)(kKW * kKW + kNoiseF + 4) * 4 + 127) / 128 * 128;   // kernel | noise | kid nid ds scale
 constexpr size_t kSmemBytes = kStageOff + (size_t)kConsumerWarps * kStageBytes;
@@ -74,7 +74,9 @@ struct TmaArgs {
     const float* pool;
     const int* nidx;
     float* lr;
-    long long nbands;
+    long long nbands;        // work items: bands x column blocks
+    int nblk;                // 256-column blocks per band (W / 256): a wider band is walked block by block, interior
+                             // block edges read real neighbour pixels, only the outer ones replicate
     int C, H, Ho, Wo;
     int nchunks;      // H/8 + 1
     int noise_mode;
@@ -111,10 +113,8 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
     }
     __syncthreads();
 
-    // stream (blockIdx, s) owns bands b0, b0 + G, b0 + 2G, ...; (n, c) = divmod(band, C) advance incrementally
+    // stream (blockIdx, s) owns items b0, b0 + G, b0 + 2G, ...; item = band * nblk + block, band = n * C + c
     const long long G = (long long)gridDim.x * kStreams;
-    const long long Gn = G / a.C;
-    const int Gc = (int)(G - Gn * a.C);
 
     if (warp >= kConsumerWarps) {
         // ============ TMA producers: warp kConsumerWarps + s, lane 0, feeds the ring of stream s ============
@@ -123,8 +123,15 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
         if (lane != 0 || MODE == 2) return;
         const int s = warp - kConsumerWarps;
         long long band = (long long)blockIdx.x * kStreams + s;
-        long long pn = band / a.C;
-        int pc = (int)(band - pn * a.C);
+        long long pn = 0;
+        int pc = 0, px = 0;
+        auto locate = [&]() {
+            const long long bd = band / a.nblk;
+            px = (int)(band - bd * a.nblk) * 128 - kLeftF / 2;
+            pn = bd / a.C;
+            pc = (int)(bd - pn * a.C);
+        };
+        locate();
         int chunk = 0, slot = 0;
         uint32_t par = 1;                                // fresh barriers: waiting on parity 1 passes
         const uint32_t sfull = full0 + 8 * s * kDepth, sempty = empty0 + 8 * s * kDepth;
@@ -144,20 +151,20 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
                                 y0 + kS * chunk - kPad, pc, 0, sfull + 8 * slot);
                     if (++slot == kDepth) { slot = 0; par ^= 1; }
                 }
-                band += G; pn += Gn; pc += Gc;
-                if (pc >= a.C) { pc -= a.C; ++pn; }
+                band += G;
+                locate();
             }
             return;
         }
         while (band < a.nbands) {
             mbar_wait_relaxed(sempty + 8 * slot, par);
             mbar_arrive_expect_tx(sfull + 8 * slot, kChunkBytes);
-            tma_load_4d_hint(smem_u32(sring + (size_t)slot * kChunkF), &tmap, -(kLeftF / 2), kS * chunk - kPad, pc,
+            tma_load_4d_hint(smem_u32(sring + (size_t)slot * kChunkF), &tmap, px, kS * chunk - kPad, pc,
                              (int)pn, sfull + 8 * slot, policy);
             if (++slot == kDepth) { slot = 0; par ^= 1; }
             if (++chunk == a.nchunks) {
-                chunk = 0; band += G; pn += Gn; pc += Gc;
-                if (pc >= a.C) { pc -= a.C; ++pn; }
+                chunk = 0; band += G;
+                locate();
             }
         }
         return;
@@ -167,8 +174,7 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
     const int s = warp >> 1, half = warp & 1;
     const int ly = lane & 7, gx = lane >> 3;
     const int g = half * 4 + gx;                 // group of 4 output columns: X = 4g .. 4g+3
-    const int ngroups = a.Wo >> 2;
-    const bool left_edge = g == 0, right_edge = g == ngroups - 1;
+    bool left_edge = false, right_edge = false;   // per item: group 0 of block 0 / group 7 of the last block
     const float* sring = ring + (size_t)s * kDepth * kChunkF;
     const uint32_t sfull = full0 + 8 * s * kDepth, sempty = empty0 + 8 * s * kDepth;
     const int nsteps = a.nchunks + 1;
@@ -213,20 +219,22 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
             if (a.noise_mode == KMSR_NOISE_SIGMA) cp4(fst_u32 + 4, a.sigma + (long long)kid * a.C + c);
         }
     };
-    auto stage_noise = [&](int nid, int c) {             // all lanes: Ho rows x 4 chunks of 16 bytes
-        const float* src = a.pool + ((long long)nid * a.C + c) * ohw + 16 * half;
+    auto stage_noise = [&](int nid, int c, int blk) {    // all lanes: Ho rows x 4 chunks of 16 bytes
+        const float* src = a.pool + ((long long)nid * a.C + c) * ohw + 32 * blk + 16 * half;
         for (int j = lane; j < 4 * a.Ho; j += 32) cp16(nst_u32 + 16 * j, src + (long long)(j >> 2) * a.Wo + 4 * (j & 3));
     };
 
     long long band = (long long)blockIdx.x * kStreams + s;
-    long long n = band / a.C;
-    int c = (int)(band - n * a.C);
+    // item -> (patch n, band c, column block): decoded where needed rather than carried (the kernel sits at its register cap)
+    const int NBK = STATS ? 1 : a.nblk;          // fused statistics run on 256-wide bands only (tma_shape_ok)
+    auto patch_of = [&](long long it) { return it / NBK / a.C; };
+    auto band_of = [&](long long it) { return (int)((it / NBK) % a.C); };
     if (lane == 0) { ist[0] = 0; ist[1] = 0; fst[0] = 0.0f; fst[1] = 1.0f; }
     __syncwarp();
     if (band < a.nbands) {
-        if (lane == 0) stage_indices(n);
+        if (lane == 0) stage_indices(patch_of(band));
         commit(); wait_all(); __syncwarp();
-        stage_kernel(ist[0], c);
+        stage_kernel(ist[0], band_of(band));
         commit();
     }
 
@@ -249,14 +257,20 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
         const float ds = fst[0], scale = fst[1];
         const int nid = ist[1];
         __syncwarp();                              // staging area read: it may be refilled from here on
-        if (noisy) { stage_noise(nid, c); commit(); }
-        float* out = a.lr + band * ohw + 4 * g + ox_mine;
+        float* out;
+        {
+            const long long bd = band / NBK;                 // band index n * C + c
+            const int blk = (int)(band - bd * NBK);
+            if (noisy) { stage_noise(nid, (int)(bd % a.C), blk); commit(); }
+            left_edge = g == 0 && blk == 0;
+            right_edge = g == 7 && blk == NBK - 1;
+            out = a.lr + bd * ohw + 32 * blk + 4 * g + ox_mine;
+        }
         const float* nzs = nst + 4 * gx + ox_mine;
-        // next band of this stream
+        // next item of this stream
         const bool has_next = band + G < a.nbands;
-        long long nn = n + Gn;
-        int nc = c + Gc;
-        if (nc >= a.C) { nc -= a.C; ++nn; }
+        const long long nn = patch_of(band + G);
+        const int nc = band_of(band + G);
 
         float pv = 0.0f;
         u64 npv2 = 0ull;
@@ -498,7 +512,6 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
                 a.stat_part[(band * 2 + half) * 2 + 1] = t2;
             }
         }
-        n = nn; c = nc;
     }
 }
 
@@ -509,8 +522,9 @@ bool tma_shape_ok(const DegradeArgs& a, const char** why) {
     *why = "";
     if (g.kh != kK || g.kw != kK || g.stride != kS || g.KH != kKW) { *why = "needs k=13 and factor 8 (box mean)"; return false; }
     if (a.pad_mode != KMSR_PAD_REPLICATE) { *why = "needs replicate padding"; return false; }
-    if (a.W != 256) { *why = "needs W == 256"; return false; }
-    if (a.H < 8 || a.H % 8 != 0 || a.H > 8 * kMaxHo) { *why = "needs H % 8 == 0 and H <= 256"; return false; }
+    if (a.W < 256 || a.W % 256 != 0 || a.W > 8192) { *why = "needs W a multiple of 256"; return false; }
+    if ((a.patch_offsets || a.stat_part) && a.W != 256) { *why = "scene windows / fused statistics need W == 256"; return false; }
+    if (a.H < 8 || a.H % 8 != 0 || a.H > 8 * kMaxHo) { *why = "needs H % 8 == 0 and H <= 512"; return false; }
     if (a.patch_offsets) {
         if (a.scene_h <= 0 || a.scene_w <= 0) { *why = "patch_offsets without scene extents (use kmsr_degrade_windows)"; return false; }
         if (a.x_multiple % 4 != 0) { *why = "window columns not promised to be multiples of 4"; return false; }
@@ -544,7 +558,8 @@ int launch_degrade_tma(const DegradeArgs& a, cudaStream_t st) {
 
     TmaArgs t;
     t.comp = a.comp; t.dsum = a.dsum; t.kidx = a.kidx; t.sigma = a.sigma; t.pool = a.pool; t.nidx = a.nidx;
-    t.lr = a.lr; t.nbands = a.N * a.C; t.C = a.C; t.H = a.H; t.Ho = a.g.Ho; t.Wo = a.g.Wo;
+    t.nblk = a.W / 256;
+    t.lr = a.lr; t.nbands = a.N * a.C * t.nblk; t.C = a.C; t.H = a.H; t.Ho = a.g.Ho; t.Wo = a.g.Wo;
     t.nchunks = a.H / 8 + 1; t.noise_mode = a.noise_mode;
     t.offs = a.patch_offsets; t.sH = a.sH;
 

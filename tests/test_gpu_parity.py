@@ -729,7 +729,37 @@ def test_content_adaptive_pick_feeds_the_fused_kernel(K, golden, synth, bank):
         check_pixels(lr[i].numpy(), ref[i], hr[i], ex, noise=sb[kidx[i]][:, None, None].astype(np.float64) * pool[nidx[i]], name=f"adaptive {i}")
 
 
+def test_wide_bands_through_the_headline_kernel(K, synth, bank):
+    """W = 512 / 768: the TMA kernel walks a band in 256-column blocks (interior block edges read real neighbours, only the
+    outer ones replicate), noise tile and output offsets follow the block; H up to 512."""
+    kb, sb = bank
+    rs = np.random.RandomState(77)
+    for h, w in ((128, 512), (512, 512), (40, 768)):
+        n = 3
+        hr = (rs.standard_normal((n, 5, h, w)) * 3.0 + np.array([80, 70, 50, 25, 8])[None, :, None, None]).astype(np.float32)
+        pool = (rs.standard_normal((7, 5, h // 8, w // 8)) * 0.5).astype(np.float32)
+        kidx = np.array([3, 9, 0], dtype=np.int32)
+        nidx = np.array([6, 0, 2], dtype=np.int32)
+        lr = K.ops.degrade_batch(torch.from_numpy(hr).cuda(), torch.from_numpy(kb).cuda(), kidx=kidx, sigma=torch.from_numpy(sb),
+                                 pool=torch.from_numpy(pool).cuda(), nidx=nidx, factor=8, noise_mode="sigma").cpu().numpy()
+        assert K.lib.last_algo() == "tma"
+        ref = orc.multi_kernel_pairs(hr, kb, sb, pool, kidx, nidx, 8)
+        for i in range(n):
+            ex = exact_degrade(hr[i], kb[kidx[i]], 8)
+            check_pixels(lr[i], ref[i], hr[i], ex, noise=sb[kidx[i]][:, None, None].astype(np.float64) * pool[nidx[i]],
+                         name=f"wide {h}x{w} #{i}")
+        # NaN footprint across a block edge
+        hn = hr.copy()
+        hn[0, 2, h // 2, 255] = np.nan
+        hn[1, 0, 0, 256] = np.nan
+        ln = K.ops.degrade_batch(torch.from_numpy(hn).cuda(), torch.from_numpy(kb[1]).cuda(), factor=8).cpu().numpy()
+        for i in range(2):
+            r = orc.apply_kernel_degradation(torch.from_numpy(hn[i]), torch.from_numpy(kb[1]), 8).numpy()
+            assert np.array_equal(np.isnan(ln[i]), np.isnan(r)), (h, w, i)
+
+
 @pytest.mark.parametrize("h,w,k,s,algo", [(64, 256, 13, 8, "tma"), (8, 256, 13, 8, "tma"), (16, 256, 13, 8, "tma"), (248, 256, 13, 8, "tma"),
+                                          (64, 512, 13, 8, "tma"),
                                           (96, 128, 11, 4, "stream"), (8, 64, 15, 8, "stream"), (40, 512, 21, 2, "stream"),
                                           (24, 768, 13, 8, "stream")])
 def test_non_square_and_short_patches(K, synth, bank, h, w, k, s, algo):
