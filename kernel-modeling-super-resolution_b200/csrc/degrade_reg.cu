@@ -293,6 +293,8 @@ template <int K>
 int launch_reg_k(const DegradeArgs& a, RegArgs& t, int S, cudaStream_t st) {
     // factor 4 with 4 x 4 outputs per thread and 64-thread CTAs (the same staged tile per half as many threads) was
     // measured 15-30 % slower than 4 x 2 / 128 threads (r62): four warps per SM do not hide the shared-memory latency
+    // hoisting all composite-kernel rows of an input row ahead of the FFMA2 blocks (k <= 15: 64 more registers, 245-255
+    // in all) measured 3-20 % slower (r74).
     // factor 2 with 8 x 2 outputs per thread and 256-thread CTAs (twice the warps per staged tile) measured no faster at
     // P = 256 and 15-20 % slower at P = 128 (r69); tap-major FFMA2 ordering is what the compiler already emits (r68).
     // factor 8 (2 x 1 outputs per thread) was measured at half the streaming kernel's speed on every cell, 64-wide
