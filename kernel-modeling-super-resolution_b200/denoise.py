@@ -3,7 +3,8 @@
 `denoise_band_float_nlm(img_float, h_factor=1.15, patch_size=7, patch_distance=11, verbose=True)` keeps the
 reference contract (denoise.py:34-68): one 2-D band in, `(denoised, estimated_sigma)` out, NaN pixels filled with
 the band's nanmean for the computation and restored afterwards, an all-NaN band returned as it is with sigma 0.0.
-`process_nc_file(file_path, output_dir, h_factor=1.8, plot=False, verbose=True)` keeps the folder-level contract
+`process_nc_file(file_path, output_dir, h_factor=1.8, plot=False, verbose=True)` (and `batch_denoise`, the loop of
+batch_denoise.py) keeps the folder-level contract
 (denoise.py:150-262): reads the five `geophysical_data` bands (zeros -> NaN, :31), denoises each, copies the file to
 `<stem>_denoised.<ext>` and adds a `denoised` group with the per-band `<band>_sigma` / `<band>_h` attributes and
 their averages; returns `(success, output_path, error_msg)` and never raises.  `denoise_bands` is the additive
@@ -86,3 +87,36 @@ def process_nc_file(file_path, output_dir, h_factor=1.8, plot=False, verbose=Tru
         if verbose:
             print(error_msg)
         return False, None, error_msg
+
+
+def batch_denoise(input_dir, output_dir=None, h_factor=1.8, pattern="*.nc", verbose=False):
+    """The loop of denoise/batch_denoise.py:16-93 as a function: every file of `input_dir` matching `pattern` goes
+    through process_nc_file into `output_dir` (default `<input_dir>_denoised`, :39-42); failures are collected, not
+    raised (:60-93).  Returns (success_count, failed_files) with failed_files = [(file name, error message)].
+    `*.npz` group containers are picked up next to `*.nc` when the pattern is the default one."""
+    import glob
+    input_dir = str(input_dir)
+    if not os.path.isdir(input_dir):
+        print(f"error: input directory does not exist: {input_dir}")
+        return 0, []
+    if output_dir is None:
+        output_dir = os.path.join(os.path.dirname(os.path.abspath(input_dir)), f"{os.path.basename(os.path.abspath(input_dir))}_denoised")
+    os.makedirs(str(output_dir), exist_ok=True)
+    files = sorted(glob.glob(os.path.join(input_dir, pattern)))
+    if pattern == "*.nc":
+        files += sorted(glob.glob(os.path.join(input_dir, "*.npz")))
+    if not files:
+        print(f"error: no file matching '{pattern}' in {input_dir}")
+        return 0, []
+    print(f"batch denoise: {len(files)} files, h_factor={h_factor}, patch_size=7, patch_distance=11 -> {output_dir}")
+    success_count, failed_files = 0, []
+    for i, f in enumerate(files, 1):
+        if verbose:
+            print(f"\n[{i}/{len(files)}]")
+        ok, _, err = process_nc_file(f, output_dir, h_factor=h_factor, plot=False, verbose=verbose)
+        if ok:
+            success_count += 1
+        else:
+            failed_files.append((os.path.basename(f), err))
+    print(f"done: {success_count}/{len(files)} succeeded, {len(failed_files)} failed")
+    return success_count, failed_files

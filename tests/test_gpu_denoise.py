@@ -12,6 +12,8 @@ sigma: <= 1e-5 relative to the float64 evaluation of the estimator, and <= 1e-5 
 the float32 evaluation (float32 pywt at radiance level 80 is itself ~6e-5 off on a sigma of 0.05).  The NLM check
 is run with the sigma the GPU estimated (already held to 1e-5), so it isolates the NLM arithmetic.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -162,6 +164,15 @@ def test_dropin_signatures(K, tmp_path, capsys):
     assert np.array_equal(patch_io.read_group_bands(path, "geophysical_data"), geo)
     ok, path, err = K.den.process_nc_file(str(tmp_path / "missing.npz"), str(tmp_path / "out"), verbose=False)
     assert not ok and path is None and err.startswith("Error:")
+    # batch_denoise.py's loop: two good files and one that cannot be read
+    indir = tmp_path / "goci"
+    indir.mkdir()
+    for j in range(2):
+        patch_io.write_groups(str(indir / f"p_{j}.npz"), {"geophysical_data": {b: geo[c] + j for c, b in enumerate(BAND_NAMES)}})
+    (indir / "broken.npz").write_bytes(b"not a zip")
+    okc, failed = K.den.batch_denoise(str(indir), h_factor=1.0)
+    assert okc == 2 and [f for f, _ in failed] == ["broken.npz"]
+    assert sorted(os.listdir(str(tmp_path / "goci_denoised"))) == ["p_0_denoised.npz", "p_1_denoised.npz"]
     # the denoised group feeds D_build_noise_pool's `geophysical_data - denoised` (D:84-88)
     g0 = np.where(geo != 0, geo, np.nan)
     noise = K.ops.crop_sub(torch.from_numpy(g0).cuda(), torch.from_numpy(den5).cuda(), [8], [8], 32).cpu().numpy()[0]
