@@ -80,6 +80,7 @@ struct TmaArgs {
     int C, H, Ho, Wo;
     int nchunks;      // H/8 + 1
     int noise_mode;
+    int fence;               // CTA-scope fence between a step's loads and the release of its chunk (see loads_performed)
     const long long* offs;   // scene windows: element offset of window n in band 0 (else nullptr)
     long long sH;            // scene row stride in elements (windows only)
     double* stat_part;       // STATS: [nbands][2 warps][sum x, sum x^2] (data_mean_std.py:32-33 fused), else nullptr
@@ -292,6 +293,13 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
 #pragma unroll
         for (int x = 0; x < 4; ++x) A0[x] = A1[x] = A2[x] = 0ull;
 
+        // An mbarrier.arrive does not wait for the warp's outstanding shared-memory loads: before a chunk is handed back
+        // to the producer the LDS just issued must have been performed, or a refill could land in the slot first (the
+        // generic streaming kernel showed exactly that once its interior path got shorter, r77).  KMSR_TMA_NOFENCE=1
+        // (bench only) drops the fence to measure what it costs.
+        auto loads_performed = [&]() {
+            if (a.fence) __threadfence_block();
+        };
         // One step = one 8-row chunk.  Row 8i+ly meets output row Y = i - q through composite row
         // u = ly + 8q: F starts output row i (q = 0), M continues row i-1 (q = 1), L completes row i-2
         // (q = 2) and is written.  The three accumulator sets rotate roles by renaming (3x unrolled).
@@ -318,6 +326,7 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
             // this chunk is no longer needed once its rows sit in registers -- except the last one,
             // which the bottom-halo step reads again
             const bool release = i < a.nchunks - 1;
+            loads_performed();
             __syncwarp();
             if (release && lane == 0 && MODE != 2) mbar_arrive(sempty + 8 * slot);
             if (release) { if (++slot == kDepth) { slot = 0; par ^= 1; } }
@@ -414,6 +423,7 @@ degrade_tma_kernel(const __grid_constant__ CUtensorMap tmap, const TmaArgs a) {
                 const ulonglong2 t = reinterpret_cast<const ulonglong2*>(src)[j];
                 E[2 * j] = t.x; E[2 * j + 1] = t.y;
             }
+            loads_performed();
             __syncwarp();
             if (lane == 0 && MODE != 2) mbar_arrive(sempty + 8 * slot);
             if (++slot == kDepth) { slot = 0; par ^= 1; }
@@ -561,6 +571,8 @@ int launch_degrade_tma(const DegradeArgs& a, cudaStream_t st) {
     t.nblk = a.W / 256;
     t.lr = a.lr; t.nbands = a.N * a.C * t.nblk; t.C = a.C; t.H = a.H; t.Ho = a.g.Ho; t.Wo = a.g.Wo;
     t.nchunks = a.H / 8 + 1; t.noise_mode = a.noise_mode;
+    static const int nofence = [] { const char* e = getenv("KMSR_TMA_NOFENCE"); return e ? atoi(e) : 0; }();
+    t.fence = nofence ? 0 : 1;
     t.offs = a.patch_offsets; t.sH = a.sH;
 
     int dev = 0, sms = 0;

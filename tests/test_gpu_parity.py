@@ -383,6 +383,29 @@ def test_register_tile_kernel(K, synth, k, s, h, w):
         assert np.array_equal(np.isnan(ln[i]), np.isnan(ref)), (k, s, h, w, i)
 
 
+def test_streaming_interior_path_equals_general_path(K, synth, monkeypatch):
+    """The interior fast path of degrade_stream (one chunk in, one chunk out per step) must give the bits of the general
+    path (KMSR_STREAM_NOFAST=1) on every <K, S, TX> variant, run to run -- the check that caught a chunk being handed
+    back to the producer before the warp's queued shared-memory loads had read it -- and both must agree with the
+    tiled kernel."""
+    torch.manual_seed(5)
+    for k in (11, 13, 15, 21, 31):
+        kd = torch.from_numpy(synth.softmax_kernels(k, 7)).cuda()
+        for s in (4, 8):
+            for (h, w) in ((64, 64), (128, 128), (96, 512), (256, 1024)):
+                n = 48 if h * w <= 128 * 128 else 16
+                hr = torch.randn((n, 5, h, w), device="cuda") * 3 + 50
+                for pad in ("replicate", "zero"):
+                    monkeypatch.setenv("KMSR_STREAM_NOFAST", "1")
+                    g = K.ops.degrade_batch(hr, kd, factor=s, pad_mode=pad, algo="stream")
+                    monkeypatch.setenv("KMSR_STREAM_NOFAST", "0")
+                    for _ in range(3):
+                        f = K.ops.degrade_batch(hr, kd, factor=s, pad_mode=pad, algo="stream")
+                        assert torch.equal(f, g), (k, s, h, w, pad)
+                    t = K.ops.degrade_batch(hr, kd, factor=s, pad_mode=pad, algo="tiled")
+                    assert float((f - t).abs().max()) <= 1e-4 * 25.0, (k, s, h, w, pad)
+
+
 def test_nan_propagation_matches_reference(K, synth, bank):
     """A NaN pixel poisons exactly the LR pixels whose (clamped) window contains it."""
     kb, _ = bank
