@@ -60,9 +60,7 @@ struct Cfg {
     // step): unrolling 2 or 4 steps of the larger shapes was measured 3-9 % slower (code size), r49
     static constexpr int U = Q <= kRenameQ ? Q : 1;
     static constexpr int GC = cgcd(Q, U);                        // cycles of the rotation by U
-    // interior fast path (second copy of the unrolled step block): +7..27 % everywhere except k = 31 at factor 4, whose
-    // block already spills and lost 2-9 % to the larger code (r78)
-    static constexpr bool FAST = !(K == 31 && S == 4);
+    static constexpr bool PERSTEP = S == 4 && K >= 21;           // interior / general fetch chosen per step instead of per block
     static_assert(K % 2 == 1 && (S == 2 || S == 4 || S == 8), "odd kernel, factor 2/4/8");
 };
 
@@ -391,9 +389,12 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
             for (int x = 0; x < kTX; ++x) A[JO][x] = 0ull;                 // becomes the fresh set of step i + 1
         };
 
-        // A step = fetch this lane's row (general: clamped rows, any number of chunks to wait for / release; fast: the
-        // interior steps, where exactly one chunk arrives and one leaves) + `body` (edges, pivot, FFMA2, reduce, store).
-        auto step = [&](auto sh_tag, const int i) {
+        // A step = fetch this lane's row + `body` (edges, pivot, FFMA2, reduce, store).  Two ways to fetch:
+        // general -- clamped rows, any number of chunks to wait for / release (band top and bottom);
+        // interior -- every row of the step lies inside the image and the output row exists.  Chunk accounting is then
+        // fixed: rows S*i - PAD .. S*i - PAD + S - 1 start `o_rows` rows into chunk `rel` (slot rslot) and spill into the
+        // next one, which is the single chunk this step waits for; chunk `rel` is released once the rows are in registers.
+        auto fetch_general = [&](const int i, float (&e)[G::LOADF]) -> bool {
             // ---- rows this step needs: padded rows S*i .. S*i+S-1 = image rows S*i - PAD + ly ----
             const int rr_raw = S * i + ly - G::PAD;
             const int rr = min(max(rr_raw, 0), a.H - 1);
@@ -413,53 +414,67 @@ degrade_stream_kernel(const __grid_constant__ CUtensorMap tmap, const StreamArgs
                 if (!isfinite(pv)) pv = 0.0f;
                 npv2 = pack2(-pv, -pv);
             }
-            float e[G::LOADF];
 #pragma unroll
             for (int j = 0; j < G::LOADF / 4; ++j) {
                 const float4 t = reinterpret_cast<const float4*>(src)[j];
                 e[4 * j + 0] = t.x; e[4 * j + 1] = t.y; e[4 * j + 2] = t.z; e[4 * j + 3] = t.w;
             }
             // release the chunks no later step needs (all of them after the item's last step)
-            {
-                const int lo_next = i + 1 < nsteps ? min(max(S * (i + 1) - G::PAD, 0), a.H - 1) / S : a.nchunks;
-                release_after_loads(lo_next - rel);
-            }
-            body(sh_tag, i, e, row_ok);
+            const int lo_next = i + 1 < nsteps ? min(max(S * (i + 1) - G::PAD, 0), a.H - 1) / S : a.nchunks;
+            release_after_loads(lo_next - rel);
+            return row_ok;
         };
-
-        // Interior steps: every row of the step lies inside the image and the output row exists.  Chunk accounting is then
-        // fixed: rows S*i - PAD .. S*i - PAD + S - 1 start `o_rows` rows into chunk `rel` (slot rslot) and spill into the
-        // next one, which is the single chunk this step waits for; chunk `rel` is released once the rows are in registers.
         constexpr int o_rows = (S - G::PAD % S) % S;
         const bool lane_hi = o_rows + ly >= S;
         const int rowin = o_rows + ly - (lane_hi ? S : 0);
-        auto fast = [&](auto sh_tag, const int i) {
+        auto fetch_interior = [&](float (&e)[G::LOADF]) {
             mbar_wait(sfull + 8 * wslot, wpar);
             if (++wslot == D) { wslot = 0; wpar ^= 1; }
             ++wai;
             int slot = rslot + (lane_hi ? 1 : 0);
             if (slot >= D) slot -= D;
             const float* src = reinterpret_cast<const float*>(sring + (size_t)slot * a.slotBytes) + rowin * a.pitchF + lane_off;
-            float e[G::LOADF];
 #pragma unroll
             for (int j = 0; j < G::LOADF / 4; ++j) {
                 const float4 t = reinterpret_cast<const float4*>(src)[j];
                 e[4 * j + 0] = t.x; e[4 * j + 1] = t.y; e[4 * j + 2] = t.z; e[4 * j + 3] = t.w;
             }
             release_after_loads(1);
-            body(sh_tag, i, e, true);
         };
         const int i_lo = a.nofast ? (1 << 30) : max((G::PAD + S - 1) / S, G::Q - 1);      // first step with all rows >= 0 and an output row
         // last step whose rows are all <= H - 1 AND whose successor no longer needs the step's first chunk (the next
         // step's first row, S (i + 1) - PAD, must not be clamped back into it: matters when PAD is a multiple of S)
         const int i_hi = (a.H - 1 + G::PAD - S) / S;
+        // per block of U steps (two copies of the block: fastest where the code fits) or per step (one copy, both fetches
+        // inline: +9-15 % for k = 31 / 21 at factor 4, whose blocks are large and spill; 3-10 % slower elsewhere, r79)
+        auto step_general = [&](auto sh_tag, const int i) {
+            float e[G::LOADF];
+            const bool row_ok = fetch_general(i, e);
+            body(sh_tag, i, e, row_ok);
+        };
+        auto step_interior = [&](auto sh_tag, const int i) {
+            float e[G::LOADF];
+            fetch_interior(e);
+            body(sh_tag, i, e, true);
+        };
+        auto step_any = [&](auto sh_tag, const int i) {
+            float e[G::LOADF];
+            bool row_ok = true;
+            if (i >= i_lo && i <= i_hi) fetch_interior(e);
+            else row_ok = fetch_general(i, e);
+            body(sh_tag, i, e, row_ok);
+        };
 
         // U consecutive steps run with compile-time set indices (renaming); when U < Q the sets are then rotated by U
         // positions by value, once per U steps instead of once per step
 #pragma unroll 1
         for (int i = 0; i < nsteps; i += G::U) {
-            if (G::FAST && i >= i_lo && i + G::U - 1 <= i_hi) Unroll<0, G::U>::run(fast, i, nsteps);
-            else Unroll<0, G::U>::run(step, i, nsteps);
+            if constexpr (G::PERSTEP) {
+                Unroll<0, G::U>::run(step_any, i, nsteps);
+            } else {
+                if (i >= i_lo && i + G::U - 1 <= i_hi) Unroll<0, G::U>::run(step_interior, i, nsteps);
+                else Unroll<0, G::U>::run(step_general, i, nsteps);
+            }
             if constexpr (G::U != G::Q) {
                 // in-place rotation A[m] <- A[(m + U) mod Q]: gcd(Q, U) cycles, one spare set
                 constexpr int GC = G::GC;
