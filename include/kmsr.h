@@ -240,6 +240,22 @@ KMSR_API int kmsr_denoise_nlm(const float* x, int64_t N, int C, int H, int W, in
                               double h_factor, int patch_size, int patch_distance, float* out, double* sigma,
                               void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- f2: learned kernel pick (SelectorNet, muti_kernel/train_gemini.py:14-39) ----------------------
+ * logits [N, 10] of the selector CNN for patches x [N, 5, H, W] (contiguous): three 3x3 / stride-2 / pad-1
+ * convolutions (5 -> 32 -> 64 -> 128) with eval-mode BatchNorm folded in and ReLU, global average pooling, a
+ * 128 -> 10 linear layer.  argmax over the 10 logits is the kernel index (kidx) of kmsr_degrade_*.
+ * The convolutions run as 3xTF32-split tensor-core MMAs (fp32-level accuracy).  Weight blobs w1 / w2 / w3 are
+ * prepared on the host (kmsr_b200/selector.py: BN fold, [chunk][channel block][hi|lo][tap][8][8 NT + 8] layout,
+ * TF32 hi / lo split), kmsr_selector_weight_floats(cin, cout) floats each, 16-byte aligned; b1 / b2 / b3 are
+ * the folded biases [32] / [64] / [128]; fc_w [10, 128], fc_b [10].  N <= 65535 per call.
+ * workspace: kmsr_selector_workspace_bytes(N, H, W), 256-byte aligned (the two intermediate activations). */
+KMSR_API int64_t kmsr_selector_weight_floats(int cin, int cout);
+KMSR_API int64_t kmsr_selector_workspace_bytes(int64_t N, int H, int W);
+KMSR_API int kmsr_selector_logits(const float* x, int64_t N, int H, int W,
+                                  const float* w1, const float* b1, const float* w2, const float* b2,
+                                  const float* w3, const float* b3, const float* fc_w, const float* fc_b,
+                                  float* logits, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------
  * Launch counter: number of kernels this library launched on the calling process since load.   */
 KMSR_API int64_t kmsr_launch_count(void);

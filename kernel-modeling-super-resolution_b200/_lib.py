@@ -64,6 +64,9 @@ SIGNATURES = {
     "kmsr_denoise_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "kmsr_estimate_sigma": (_i32, [_vp, _i64, _i32, _i32, _i32, _i64, _vp, _vp, _i64, _vp]),
     "kmsr_denoise_nlm": (_i32, [_vp, _i64, _i32, _i32, _i32, _i64, _f64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "kmsr_selector_weight_floats": (_i64, [_i32, _i32]),
+    "kmsr_selector_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "kmsr_selector_logits": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "kmsr_launch_count": (_i64, []),
     "kmsr_last_algo": (C.c_char_p, []),
 }

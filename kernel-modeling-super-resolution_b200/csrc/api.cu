@@ -39,6 +39,10 @@ int launch_estimate_sigma(const float*, long long, int, int, int, long long, dou
 int launch_nlm(const float*, long long, int, int, int, long long, const double*, const double*, double, int, float*,
                cudaStream_t);
 bool nlm_shape_ok(int, int, const char**);
+long long selector_wsplit_floats(int, int);
+long long selector_workspace(long long, int, int);
+int launch_selector(const float*, long long, int, int, const float*, const float*, const float*, const float*, const float*,
+                    const float*, const float*, const float*, float*, void*, long long, cudaStream_t);
 
 }  // namespace kmsr
 
@@ -354,6 +358,33 @@ KMSR_API int kmsr_denoise_nlm(const float* x, int64_t N, int C, int H, int W, in
     if (rc != KMSR_OK) return rc;
     return launch_nlm(x, N, C, H, W, x_stride_n, reinterpret_cast<const double*>(workspace), sigma, h_factor, patch_distance,
                       out, (cudaStream_t)stream);
+}
+
+KMSR_API int64_t kmsr_selector_weight_floats(int cin, int cout) {
+    if (cin < 1 || cout < 32 || cout % 32 != 0) {
+        set_error("selector_weight_floats: cin=%d cout=%d", cin, cout);
+        return KMSR_E_INVALID;
+    }
+    return selector_wsplit_floats(cin, cout);
+}
+
+KMSR_API int64_t kmsr_selector_workspace_bytes(int64_t N, int H, int W) {
+    if (N < 0 || H < 1 || W < 1) {
+        set_error("selector_workspace_bytes: N=%lld H=%d W=%d", (long long)N, H, W);
+        return KMSR_E_INVALID;
+    }
+    return selector_workspace(N, H, W);
+}
+
+KMSR_API int kmsr_selector_logits(const float* x, int64_t N, int H, int W, const float* w1, const float* b1, const float* w2,
+                                  const float* b2, const float* w3, const float* b3, const float* fc_w, const float* fc_b,
+                                  float* logits, void* workspace, int64_t workspace_bytes, void* stream) {
+    KMSR_REQUIRE(N >= 0 && H >= 1 && W >= 1, KMSR_E_INVALID, "selector_logits: N=%lld H=%d W=%d", (long long)N, H, W);
+    if (N == 0) return KMSR_OK;
+    KMSR_REQUIRE(x && w1 && b1 && w2 && b2 && w3 && b3 && fc_w && fc_b && logits && workspace, KMSR_E_INVALID,
+                 "selector_logits: null pointer");
+    return launch_selector(x, N, H, W, w1, b1, w2, b2, w3, b3, fc_w, fc_b, logits, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -5,16 +5,23 @@ convolutions with BatchNorm + ReLU, global average pool, linear layer (train_gem
 among the 10 kernels / sigma rows of the bank (train_gemini.py:107-115).  Training uses a Gumbel-softmax over the
 logits; the deterministic inference form is the hard pick `argmax(logits)` (the `hard=True`, temperature -> 0 limit).
 
-SURVEY.md lists this as a *next* row that "could stay in PyTorch": the selector below is LIBRARY code (cuDNN / cuBLAS
-through torch, fp32 with TF32 disabled so that the pick is reproducible), not a hand-written kernel; what it feeds --
-the per-patch `kidx` -- goes into the fused sm_100a degrade kernel exactly like the random pick of config 2.
+On a CUDA tensor the logits come from libkmsr's own kernels (`kmsr_selector_logits`, csrc/selector.cu): BatchNorm is
+folded into the convolution weights here on the host, the weights are laid out and split into TF32 hi / lo parts for
+the 3xTF32 tensor-core MMAs (fp32-level accuracy, so the pick does not depend on reduced precision), and the three
+convolutions, the pooling and the linear layer run as four launches.  `logits_library` keeps the torch / cuDNN fp32
+evaluation (TF32 disabled) -- the form SURVEY.md says "could stay in PyTorch" -- as the cross-check the tests use and
+for CPU tensors.  What the pick feeds -- the per-patch `kidx` -- goes into the fused sm_100a degrade kernel exactly
+like the random pick of config 2.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import _lib as L
 from . import ops, rng
 
 _BN_EPS = 1e-5            # nn.BatchNorm2d default (train_gemini.py:20)
@@ -35,6 +42,7 @@ class Selector:
         self.fc_w = t["classifier.weight"].float()
         self.fc_b = t["classifier.bias"].float()
         self.device = dev
+        self._cuda = None
 
     @classmethod
     def from_state_dict_file(cls, path: str, device=None) -> "Selector":
@@ -51,11 +59,71 @@ class Selector:
         dev = torch.device(device)
         self.layers = [tuple(p.to(dev) for p in layer) for layer in self.layers]
         self.fc_w, self.fc_b, self.device = self.fc_w.to(dev), self.fc_b.to(dev), dev
+        self._cuda = None
         return self
 
+    # ---- libkmsr path ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _tf32(a: np.ndarray) -> np.ndarray:
+        """cvt.rna.tf32.f32 on the host: round the magnitude to 10 mantissa bits, ties away from zero."""
+        b = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+        return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    def _prepare(self, dev):
+        """Fold BatchNorm (train_gemini.py:19-29, eval mode) into each convolution and build the split weight blobs
+        [chunk][channel block][hi | lo][tap][8 input channels][8 NT + 8] that conv_mma_kernel stages."""
+        blobs = []
+        for w, b, g, beta, mean, var in self.layers:
+            w64, b64 = w.double().cpu().numpy(), b.double().cpu().numpy()
+            sc = g.double().cpu().numpy() / np.sqrt(var.double().cpu().numpy() + _BN_EPS)
+            wf = (w64 * sc[:, None, None, None]).astype(np.float32)             # [cout, cin, 3, 3]
+            bf = ((b64 - mean.double().cpu().numpy()) * sc + beta.double().cpu().numpy()).astype(np.float32)
+            cout, cin = wf.shape[0], wf.shape[1]
+            nt = 8 if cout >= 64 else 4
+            chunks, nblk, ns = (cin + 7) // 8, cout // (8 * nt), 8 * nt + 8
+            hi = self._tf32(wf)
+            lo = self._tf32(wf - hi)
+            blob = np.zeros((chunks, nblk, 2, 9, 8, ns), dtype=np.float32)
+            for part, src in enumerate((hi, lo)):
+                for ch in range(chunks):
+                    c0, c1 = 8 * ch, min(8 * ch + 8, cin)
+                    for nb in range(nblk):
+                        blk = src[nb * 8 * nt:(nb + 1) * 8 * nt, c0:c1]            # [n, c, ky, kx]
+                        blob[ch, nb, part, :, :c1 - c0, :8 * nt] = blk.transpose(2, 3, 1, 0).reshape(9, c1 - c0, 8 * nt)
+            assert blob.size == L.check(int(L.lib().kmsr_selector_weight_floats(cin, cout)))
+            blobs.append((torch.from_numpy(blob.reshape(-1)).to(dev), torch.from_numpy(bf).to(dev)))
+        self._cuda = (dev, blobs, self.fc_w.to(dev).contiguous(), self.fc_b.to(dev).contiguous())
+
     @torch.no_grad()
-    def logits(self, x: torch.Tensor, batch: int = 256) -> torch.Tensor:
-        """x [N,5,H,W] float32 on this selector's device -> logits [N,10] (eval-mode BatchNorm, fp32, no TF32)."""
+    def logits(self, x: torch.Tensor, batch: int = 4096) -> torch.Tensor:
+        """x [N,5,H,W] float32 -> logits [N,10].  CUDA tensors go through libkmsr (3xTF32 tensor-core convolutions with
+        folded BatchNorm); CPU tensors through the torch fp32 evaluation."""
+        if not x.is_cuda:
+            return self.logits_library(x)
+        ops.require_cuda()
+        dev = x.device
+        if getattr(self, "_cuda", None) is None or self._cuda[0] != dev:
+            self._prepare(dev)
+        _, blobs, fc_w, fc_b = self._cuda
+        x = x.to(torch.float32).contiguous()
+        n, c, h, w = x.shape
+        assert c == 5, f"SelectorNet takes 5 bands, got {c}"
+        out = torch.empty((n, 10), dtype=torch.float32, device=dev)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for a in range(0, n, batch):
+                m = min(batch, n - a)
+                wsb = L.check(int(L.lib().kmsr_selector_workspace_bytes(m, h, w)))
+                ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                L.check(L.lib().kmsr_selector_logits(p(x[a:a + m]), m, h, w, p(blobs[0][0]), p(blobs[0][1]), p(blobs[1][0]),
+                                                     p(blobs[1][1]), p(blobs[2][0]), p(blobs[2][1]), p(fc_w), p(fc_b),
+                                                     p(out[a:a + m]), p(ws), wsb, st))
+        return out
+
+    @torch.no_grad()
+    def logits_library(self, x: torch.Tensor, batch: int = 256) -> torch.Tensor:
+        """The same forward through torch (cuDNN / cuBLAS or CPU): eval-mode BatchNorm, fp32, TF32 disabled."""
         old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False

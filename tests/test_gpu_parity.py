@@ -732,8 +732,8 @@ def test_raw_scene_keep_grid_and_windows(K, golden, synth, bank):
 
 
 def test_content_adaptive_pick_feeds_the_fused_kernel(K, golden, synth, bank):
-    """f2 on the device: selector logits (cuDNN fp32, TF32 off) equal the reference's, the argmax pick drives the
-    fused degrade + sigma-noise launch, and the result equals the oracle composition with the same picks."""
+    """f2 on the device: selector logits (libkmsr's 3xTF32 tensor-core convolutions) equal the reference's, the argmax
+    pick drives the fused degrade + sigma-noise launch, and the result equals the oracle composition with the same picks."""
     from kmsr_b200.selector import Selector, degrade_content_adaptive
     kb, sb = bank
     z = golden("selector.npz")
@@ -779,6 +779,30 @@ def test_wide_bands_through_the_headline_kernel(K, synth, bank):
         for i in range(2):
             r = orc.apply_kernel_degradation(torch.from_numpy(hn[i]), torch.from_numpy(kb[1]), 8).numpy()
             assert np.array_equal(np.isnan(ln[i]), np.isnan(r)), (h, w, i)
+
+
+def test_selector_kernels_match_the_fp32_library_forward(K, golden, synth):
+    """kmsr_selector_logits (BatchNorm folded on the host, 3xTF32-split mma convolutions, fused pooling, linear layer)
+    against the torch fp32 forward of the same weights (TF32 disabled): logits to 2e-5 of their scale, identical argmax,
+    deterministic run to run; patch sizes that leave partial tiles; the golden logits of the reference module."""
+    from kmsr_b200.selector import Selector
+    z = golden("selector.npz")
+    sel = Selector.from_npz(z, "cuda")
+    for n, h, w in ((6, 256, 256), (5, 100, 100), (3, 72, 200), (2, 17, 33)):
+        rs = np.random.RandomState(h)
+        x = torch.from_numpy((rs.standard_normal((n, 5, h, w)) * 3.0 + np.array([80, 70, 50, 25, 8])[None, :, None, None])
+                             .astype(np.float32)).cuda()
+        a = sel.logits(x)
+        b = sel.logits_library(x)
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 2e-5 * scale, (n, h, w, float((a - b).abs().max()) / scale)
+        assert torch.equal(a.argmax(1), b.argmax(1))
+        assert torch.equal(a, sel.logits(x))
+    hr = np.concatenate([synth.make_hr(4, 5100, "textured"), synth.make_hr(2, 5101, "water")])
+    lg = sel.logits(torch.from_numpy(hr).cuda()).cpu().numpy()
+    assert np.abs(lg - z["logits"][:6]).max() <= 1e-4 * np.abs(z["logits"]).max()
+    assert np.array_equal(lg.argmax(1), z["argmax"][:6])
+    assert sel.logits(torch.zeros((0, 5, 64, 64), device="cuda")).shape == (0, 10)
 
 
 @pytest.mark.parametrize("h,w,k,s,algo", [(64, 256, 13, 8, "tma"), (8, 256, 13, 8, "tma"), (16, 256, 13, 8, "tma"), (248, 256, 13, 8, "tma"),
