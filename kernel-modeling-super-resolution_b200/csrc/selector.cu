@@ -10,9 +10,9 @@
 // MMAs per product.  `mma.sync.m16n8k8.tf32` is used: a 128-pixel x 64-channel tile per CTA with K = 72 per step is
 // far below what a tcgen05 / TMEM pipeline needs to pay off, and the layer is not the bottleneck of any headline path.
 //
-// conv_mma_kernel<NT>: one CTA = 16 x 8 output pixels x (8 NT) output channels of one patch, 4 warps, each warp two
+// conv_mma_kernel<NT>: one CTA = 32 x 8 output pixels x (8 NT) output channels of one patch, 8 warps, each warp two
 // m16 tiles (4 output rows x 8 columns) x NT n8 tiles.  The input channels are walked in chunks of 8 (zero-filled
-// beyond CIN: the 5-channel first layer uses one chunk); per chunk the 33 x 17 input pixels sit in shared memory
+// beyond CIN: the 5-channel first layer uses one chunk); per chunk the 65 x 17 input pixels sit in shared memory
 // channel-last with a pitch of 10 floats (conflict-free for the stride-2 A fragments) and the pre-split weights
 // [hi | lo][tap][8 channels][8 NT + 8] (conflict-free B fragments), both double-buffered with cp.async.
 // Epilogue: bias + ReLU, NCHW store -- or, for the last layer, the per-CTA sum over its pixels (fixed order:
@@ -24,7 +24,8 @@ namespace kmsr {
 
 namespace {
 
-constexpr int kTH = 16, kTW = 8;                 // output pixels per CTA
+constexpr int kWarps = 8, kThreads = 32 * kWarps;
+constexpr int kTH = 4 * kWarps, kTW = 8;         // output pixels per CTA: four rows per warp
 constexpr int kIH = 2 * kTH + 1, kIW = 2 * kTW + 1;   // input pixels per CTA (stride 2, 3 x 3)
 constexpr int kCS = 10;                          // floats per staged pixel (8 channels + 2: bank-conflict-free at stride 2)
 constexpr int kInF = kIH * kIW * kCS;            // floats per staged input chunk
@@ -53,7 +54,7 @@ struct ConvArgs {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kThreads)
 conv_mma_kernel(const ConvArgs a) {
     constexpr int NS = 8 * NT + 8;               // weight row pitch (floats): 8 t + g hits 32 distinct banks
     constexpr int kWF = 2 * 9 * 8 * NS;          // floats per staged weight chunk (hi and lo)
@@ -69,10 +70,10 @@ conv_mma_kernel(const ConvArgs a) {
     const int g = lane >> 2, t = lane & 3;
 
     auto stage = [&](int chunk, int buf) {
-        // input: 8 channels x 33 x 17 pixels, zero outside the image and beyond CIN (cp.async src-size 0)
+        // input: 8 channels x 65 x 17 pixels, zero outside the image and beyond CIN (cp.async src-size 0)
         const float* src = a.in + (n * a.CIN + 8 * chunk) * (long long)a.H * a.W;
         const uint32_t dst = smem_u32(in_s + buf * kInF);
-        for (int e = tid; e < 8 * kIH * kIW; e += 128) {
+        for (int e = tid; e < 8 * kIH * kIW; e += kThreads) {
             const int c = e / (kIH * kIW), p = e - c * (kIH * kIW);
             const int py = p / kIW, px = p - py * kIW;
             const int gy = iy0 + py, gx = ix0 + px;
@@ -84,7 +85,7 @@ conv_mma_kernel(const ConvArgs a) {
         // weights of this chunk and channel block: contiguous, 16-byte copies
         const float* wsrc = a.wsplit + ((long long)chunk * a.nblk + nb) * kWF;
         const uint32_t wdst = smem_u32(w_s + buf * kWF);
-        for (int e = tid; e < kWF / 4; e += 128)
+        for (int e = tid; e < kWF / 4; e += kThreads)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wdst + 16u * e), "l"(wsrc + 4 * e) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -128,17 +129,26 @@ conv_mma_kernel(const ConvArgs a) {
             }
             const float* wh = ws + tap * 8 * NS;                 // hi: [tap][c][n]
             const float* wl = wh + 9 * 8 * NS;                   // lo
+            uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                const uint32_t bh0 = __float_as_uint(wh[t * NS + 8 * j + g]), bh1 = __float_as_uint(wh[(t + 4) * NS + 8 * j + g]);
-                const uint32_t bl0 = __float_as_uint(wl[t * NS + 8 * j + g]), bl1 = __float_as_uint(wl[(t + 4) * NS + 8 * j + g]);
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    mma_tf32(acc[m][j], alo[m], bh0, bh1);       // small terms first
-                    mma_tf32(acc[m][j], ahi[m], bl0, bl1);
-                    mma_tf32(acc[m][j], ahi[m], bh0, bh1);
-                }
+                bh[j][0] = __float_as_uint(wh[t * NS + 8 * j + g]); bh[j][1] = __float_as_uint(wh[(t + 4) * NS + 8 * j + g]);
+                bl[j][0] = __float_as_uint(wl[t * NS + 8 * j + g]); bl[j][1] = __float_as_uint(wl[(t + 4) * NS + 8 * j + g]);
             }
+            // three passes over the 2 NT independent accumulator tiles (small terms first): an MMA never waits for the
+            // one issued just before it
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) mma_tf32(acc[m][j], alo[m], bh[j][0], bh[j][1]);
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) mma_tf32(acc[m][j], ahi[m], bl[j][0], bl[j][1]);
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int m = 0; m < 2; ++m) mma_tf32(acc[m][j], ahi[m], bh[j][0], bh[j][1]);
         }
         __syncthreads();                                         // buffer `buf` is refilled by the stage of chunk + 2
     }
@@ -160,7 +170,7 @@ conv_mma_kernel(const ConvArgs a) {
         return;
     }
     // last layer: ReLU, then the sum over this CTA's pixels per channel, in a fixed order
-    __shared__ float red[4][64];
+    __shared__ float red[kWarps][64];
 #pragma unroll
     for (int j = 0; j < NT; ++j)
 #pragma unroll
@@ -183,7 +193,9 @@ conv_mma_kernel(const ConvArgs a) {
         }
     __syncthreads();
     if (tid < 8 * NT) {
-        const float s = ((red[0][tid] + red[1][tid]) + red[2][tid]) + red[3][tid];
+        float s = red[0][tid];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) s += red[w][tid];
         a.pool_part[(n * a.tiles + tile) * (long long)a.COUT + cbase + tid] = s;
     }
 }
@@ -223,7 +235,7 @@ int launch_conv(const ConvArgs& a, long long N, cudaStream_t st) {
     KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KMSR_REQUIRE(N <= 65535, KMSR_E_INVALID, "selector: more than 65535 patches per call");
     dim3 grid((unsigned)(a.tiles * a.nblk), (unsigned)N);
-    kern<<<grid, 128, smem, st>>>(a);
+    kern<<<grid, kThreads, smem, st>>>(a);
     KMSR_LAUNCH_CHECK("conv_mma_kernel");
     return KMSR_OK;
 }
