@@ -14,7 +14,8 @@
 // m16 tiles (4 output rows x 8 columns) x NT n8 tiles.  The input channels are walked in chunks of 8 (zero-filled
 // beyond CIN: the 5-channel first layer uses one chunk); per chunk the 65 x 17 input pixels sit in shared memory
 // channel-last with a pitch of 10 floats (conflict-free for the stride-2 A fragments) and the pre-split weights
-// [hi | lo][tap][8 channels][8 NT + 8] (conflict-free B fragments), both double-buffered with cp.async.
+// [hi | lo][tap][8 channels][8 NT + 8] (conflict-free B fragments); single-buffered, two CTAs per SM overlap
+// each other's staging (cp.async) and MMA phases.
 // Epilogue: bias + ReLU, NCHW store -- or, for the last layer, the per-CTA sum over its pixels (fixed order:
 // deterministic) that pool_fc_kernel turns into logits.
 #include "common.cuh"
@@ -28,7 +29,7 @@ constexpr int kWarps = 8, kThreads = 32 * kWarps;
 constexpr int kTH = 4 * kWarps, kTW = 8;         // output pixels per CTA: four rows per warp
 constexpr int kIH = 2 * kTH + 1, kIW = 2 * kTW + 1;   // input pixels per CTA (stride 2, 3 x 3)
 constexpr int kCS = 10;                          // floats per staged pixel (8 channels + 2: bank-conflict-free at stride 2)
-constexpr int kInF = kIH * kIW * kCS;            // floats per staged input chunk
+constexpr int kInF = (kIH * kIW * kCS + 3) / 4 * 4;   // floats per staged input chunk (the weights behind it take 16-byte copies)
 
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
@@ -54,13 +55,13 @@ struct ConvArgs {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_mma_kernel(const ConvArgs a) {
     constexpr int NS = 8 * NT + 8;               // weight row pitch (floats): 8 t + g hits 32 distinct banks
     constexpr int kWF = 2 * 9 * 8 * NS;          // floats per staged weight chunk (hi and lo)
     extern __shared__ __align__(16) float csm[];
-    float* in_s = csm;                           // [2][kInF]
-    float* w_s = csm + 2 * kInF;                 // [2][kWF]
+    float* in_s = csm;                           // [kInF]
+    float* w_s = csm + kInF;                     // [kWF]   (single-buffered: two CTAs per SM overlap each other)
     const int tile = blockIdx.x % a.tiles, nb = blockIdx.x / a.tiles;
     const long long n = blockIdx.y;
     const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
@@ -69,10 +70,10 @@ conv_mma_kernel(const ConvArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
 
-    auto stage = [&](int chunk, int buf) {
+    auto stage = [&](int chunk) {
         // input: 8 channels x 65 x 17 pixels, zero outside the image and beyond CIN (cp.async src-size 0)
         const float* src = a.in + (n * a.CIN + 8 * chunk) * (long long)a.H * a.W;
-        const uint32_t dst = smem_u32(in_s + buf * kInF);
+        const uint32_t dst = smem_u32(in_s);
         for (int e = tid; e < 8 * kIH * kIW; e += kThreads) {
             const int c = e / (kIH * kIW), p = e - c * (kIH * kIW);
             const int py = p / kIW, px = p - py * kIW;
@@ -84,7 +85,7 @@ conv_mma_kernel(const ConvArgs a) {
         }
         // weights of this chunk and channel block: contiguous, 16-byte copies
         const float* wsrc = a.wsplit + ((long long)chunk * a.nblk + nb) * kWF;
-        const uint32_t wdst = smem_u32(w_s + buf * kWF);
+        const uint32_t wdst = smem_u32(w_s);
         for (int e = tid; e < kWF / 4; e += kThreads)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wdst + 16u * e), "l"(wsrc + 4 * e) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -98,18 +99,12 @@ conv_mma_kernel(const ConvArgs a) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[m][j][r] = 0.0f;
 
-    stage(0, 0);
     for (int chunk = 0; chunk < a.chunks; ++chunk) {
-        const int buf = chunk & 1;
-        if (chunk + 1 < a.chunks) {
-            stage(chunk + 1, buf ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
+        stage(chunk);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        const float* is = in_s + buf * kInF;
-        const float* ws = w_s + buf * kWF;
+        const float* is = in_s;
+        const float* ws = w_s;
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
             const int ky = tap / 3, kx = tap - 3 * ky;
@@ -150,7 +145,7 @@ conv_mma_kernel(const ConvArgs a) {
 #pragma unroll
                 for (int m = 0; m < 2; ++m) mma_tf32(acc[m][j], ahi[m], bh[j][0], bh[j][1]);
         }
-        __syncthreads();                                         // buffer `buf` is refilled by the stage of chunk + 2
+        __syncthreads();                                         // the staging buffers are refilled by the next chunk
     }
 
     // ---- epilogue: acc[m][j] = {(row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)}: rows = output pixels, cols = channels
@@ -230,7 +225,7 @@ pool_fc_kernel(const float* __restrict__ part, int tiles, int C, float inv_area,
 template <int NT>
 int launch_conv(const ConvArgs& a, long long N, cudaStream_t st) {
     constexpr int NS = 8 * NT + 8;
-    constexpr size_t smem = (size_t)(2 * kInF + 2 * 2 * 9 * 8 * NS) * sizeof(float);
+    constexpr size_t smem = (size_t)(kInF + 2 * 9 * 8 * NS) * sizeof(float);
     auto kern = conv_mma_kernel<NT>;
     KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KMSR_REQUIRE(N <= 65535, KMSR_E_INVALID, "selector: more than 65535 patches per call");
