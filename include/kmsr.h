@@ -245,7 +245,7 @@ KMSR_API int kmsr_denoise_nlm(const float* x, int64_t N, int C, int H, int W, in
  * convolutions (5 -> 32 -> 64 -> 128) with eval-mode BatchNorm folded in and ReLU, global average pooling, a
  * 128 -> 10 linear layer.  argmax over the 10 logits is the kernel index (kidx) of kmsr_degrade_*.
  * The convolutions run as 3xTF32-split tensor-core MMAs (fp32-level accuracy).  Weight blobs w1 / w2 / w3 are
- * prepared on the host (kmsr_b200/selector.py: BN fold, [chunk][channel block][hi|lo][tap][8][8 NT + 8] layout,
+ * prepared on the host (kmsr_b200/selector.py: BN fold, fragment-major [chunk][channel block][tap][quad][lane][4] layout,
  * TF32 hi / lo split), kmsr_selector_weight_floats(cin, cout) floats each, 16-byte aligned; b1 / b2 / b3 are
  * the folded biases [32] / [64] / [128]; fc_w [10, 128], fc_b [10].  N <= 65535 per call.
  * workspace: kmsr_selector_workspace_bytes(N, H, W), 256-byte aligned (the two intermediate activations). */

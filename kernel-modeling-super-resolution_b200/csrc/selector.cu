@@ -14,7 +14,7 @@
 // m16 tiles (4 output rows x 8 columns) x NT n8 tiles.  The input channels are walked in chunks of 8 (zero-filled
 // beyond CIN: the 5-channel first layer uses one chunk); per chunk the 65 x 17 input pixels sit in shared memory
 // channel-last with a pitch of 10 floats (conflict-free for the stride-2 A fragments) and the pre-split weights
-// [hi | lo][tap][8 channels][8 NT + 8] (conflict-free B fragments); single-buffered, two CTAs per SM overlap
+// fragment-major (each lane's B values of a tap as NT conflict-free LDS.128); single-buffered, two CTAs per SM overlap
 // each other's staging (cp.async) and MMA phases.
 // Epilogue: bias + ReLU, NCHW store -- or, for the last layer, the per-CTA sum over its pixels (fixed order:
 // deterministic) that pool_fc_kernel turns into logits.
@@ -44,7 +44,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 
 struct ConvArgs {
     const float* in;        // [N, CIN, H, W]
-    const float* wsplit;    // [chunks][nblk][2 (hi, lo)][9 taps][8][8 NT + 8]  (tf32-rounded, host-prepared)
+    const float* wsplit;    // [chunks][nblk][9 taps][NT quads][32 lanes][4]  (tf32 hi / lo parts, fragment-major, host-prepared)
     const float* bias;      // [COUT]
     float* out;             // [N, COUT, Ho, Wo], or nullptr when pooling
     float* pool_part;       // [N, tiles, COUT] per-CTA channel sums (last layer), or nullptr
@@ -57,8 +57,9 @@ struct ConvArgs {
 template <int NT>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_mma_kernel(const ConvArgs a) {
-    constexpr int NS = 8 * NT + 8;               // weight row pitch (floats): 8 t + g hits 32 distinct banks
-    constexpr int kWF = 2 * 9 * 8 * NS;          // floats per staged weight chunk (hi and lo)
+    // weights arrive fragment-major: [tap][quad NT][lane 32][4]; lane (g, t) finds its 4 NT B values of a tap -- index
+    // part * 2 NT + 2 j + h for (hi | lo, n-tile j, k = t + 4 h) -- as NT conflict-free LDS.128
+    constexpr int kWF = 9 * NT * 128;            // floats per staged weight chunk (hi and lo)
     extern __shared__ __align__(16) float csm[];
     float* in_s = csm;                           // [kInF]
     float* w_s = csm + kInF;                     // [kWF]   (single-buffered: two CTAs per SM overlap each other)
@@ -74,11 +75,12 @@ conv_mma_kernel(const ConvArgs a) {
         // input: 8 channels x 65 x 17 pixels, zero outside the image and beyond CIN (cp.async src-size 0)
         const float* src = a.in + (n * a.CIN + 8 * chunk) * (long long)a.H * a.W;
         const uint32_t dst = smem_u32(in_s);
-        for (int e = tid; e < 8 * kIH * kIW; e += kThreads) {
+        const int nc = min(8, a.CIN - 8 * chunk);                 // channels of this chunk that exist (the rest stay zero)
+        for (int e = tid; e < nc * kIH * kIW; e += kThreads) {
             const int c = e / (kIH * kIW), p = e - c * (kIH * kIW);
             const int py = p / kIW, px = p - py * kIW;
             const int gy = iy0 + py, gx = ix0 + px;
-            const bool ok = 8 * chunk + c < a.CIN && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+            const bool ok = gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
             const float* s = ok ? src + ((long long)c * a.H + gy) * a.W + gx : a.in;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4u * (p * kCS + c)), "l"(s), "r"(ok ? 4 : 0)
                          : "memory");
@@ -99,6 +101,10 @@ conv_mma_kernel(const ConvArgs a) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) acc[m][j][r] = 0.0f;
 
+    if (a.CIN % 8 != 0) {                        // channels beyond CIN are never staged: zero them once
+        for (int e = tid; e < kInF; e += kThreads) in_s[e] = 0.0f;
+        __syncthreads();
+    }
     for (int chunk = 0; chunk < a.chunks; ++chunk) {
         stage(chunk);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -122,13 +128,17 @@ conv_mma_kernel(const ConvArgs a) {
                     alo[m][r] = to_tf32(v[r] - __uint_as_float(ahi[m][r]));
                 }
             }
-            const float* wh = ws + tap * 8 * NS;                 // hi: [tap][c][n]
-            const float* wl = wh + 9 * 8 * NS;                   // lo
             uint32_t bh[NT][2], bl[NT][2];
+            {
+                const float4* wq = reinterpret_cast<const float4*>(ws + tap * NT * 128) + lane;
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                bh[j][0] = __float_as_uint(wh[t * NS + 8 * j + g]); bh[j][1] = __float_as_uint(wh[(t + 4) * NS + 8 * j + g]);
-                bl[j][0] = __float_as_uint(wl[t * NS + 8 * j + g]); bl[j][1] = __float_as_uint(wl[(t + 4) * NS + 8 * j + g]);
+                for (int q = 0; q < NT / 2; ++q) {
+                    const float4 h4 = wq[q * 32], l4 = wq[(q + NT / 2) * 32];
+                    bh[2 * q][0] = __float_as_uint(h4.x); bh[2 * q][1] = __float_as_uint(h4.y);
+                    bh[2 * q + 1][0] = __float_as_uint(h4.z); bh[2 * q + 1][1] = __float_as_uint(h4.w);
+                    bl[2 * q][0] = __float_as_uint(l4.x); bl[2 * q][1] = __float_as_uint(l4.y);
+                    bl[2 * q + 1][0] = __float_as_uint(l4.z); bl[2 * q + 1][1] = __float_as_uint(l4.w);
+                }
             }
             // three passes over the 2 NT independent accumulator tiles (small terms first): an MMA never waits for the
             // one issued just before it
@@ -224,8 +234,7 @@ pool_fc_kernel(const float* __restrict__ part, int tiles, int C, float inv_area,
 
 template <int NT>
 int launch_conv(const ConvArgs& a, long long N, cudaStream_t st) {
-    constexpr int NS = 8 * NT + 8;
-    constexpr size_t smem = (size_t)(kInF + 2 * 9 * 8 * NS) * sizeof(float);
+    constexpr size_t smem = (size_t)(kInF + 9 * NT * 128) * sizeof(float);
     auto kern = conv_mma_kernel<NT>;
     KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     KMSR_REQUIRE(N <= 65535, KMSR_E_INVALID, "selector: more than 65535 patches per call");
@@ -239,11 +248,11 @@ inline int conv_out(int h) { return (h - 1) / 2 + 1; }       // (h + 2 - 3) / 2 
 
 }  // namespace
 
-// floats of the split weight blob of one layer: chunks x nblk x 2 x 9 x 8 x (8 NT + 8)
+// floats of the split weight blob of one layer: chunks x nblk x 9 taps x NT quads x 32 lanes x 4
 long long selector_wsplit_floats(int cin, int cout) {
     const int NT = cout >= 64 ? 8 : 4;
     const int chunks = (cin + 7) / 8, nblk = cout / (8 * NT);
-    return (long long)chunks * nblk * 2 * 9 * 8 * (8 * NT + 8);
+    return (long long)chunks * nblk * 9 * NT * 128;
 }
 
 long long selector_workspace(long long N, int H, int W) {

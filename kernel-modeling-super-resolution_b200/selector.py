@@ -71,7 +71,7 @@ class Selector:
 
     def _prepare(self, dev):
         """Fold BatchNorm (train_gemini.py:19-29, eval mode) into each convolution and build the split weight blobs
-        [chunk][channel block][hi | lo][tap][8 input channels][8 NT + 8] that conv_mma_kernel stages."""
+        [chunk][channel block][tap][quad][lane][4] (fragment-major, TF32 hi / lo parts) that conv_mma_kernel stages."""
         blobs = []
         for w, b, g, beta, mean, var in self.layers:
             w64, b64 = w.double().cpu().numpy(), b.double().cpu().numpy()
@@ -80,16 +80,26 @@ class Selector:
             bf = ((b64 - mean.double().cpu().numpy()) * sc + beta.double().cpu().numpy()).astype(np.float32)
             cout, cin = wf.shape[0], wf.shape[1]
             nt = 8 if cout >= 64 else 4
-            chunks, nblk, ns = (cin + 7) // 8, cout // (8 * nt), 8 * nt + 8
+            chunks, nblk = (cin + 7) // 8, cout // (8 * nt)
             hi = self._tf32(wf)
             lo = self._tf32(wf - hi)
-            blob = np.zeros((chunks, nblk, 2, 9, 8, ns), dtype=np.float32)
-            for part, src in enumerate((hi, lo)):
-                for ch in range(chunks):
-                    c0, c1 = 8 * ch, min(8 * ch + 8, cin)
-                    for nb in range(nblk):
-                        blk = src[nb * 8 * nt:(nb + 1) * 8 * nt, c0:c1]            # [n, c, ky, kx]
-                        blob[ch, nb, part, :, :c1 - c0, :8 * nt] = blk.transpose(2, 3, 1, 0).reshape(9, c1 - c0, 8 * nt)
+            # fragment-major: blob[chunk, block, tap, quad, lane, 4]; lane (g = lane >> 2, t = lane & 3) owns, per tap, the
+            # B values (part, j, h) = W_part[n = 8 (block * nt + j) + g][c = 8 chunk + t + 4 h][tap] at index part * 2 nt + 2 j + h
+            wpad = np.zeros((2, cout, 8 * chunks, 9), dtype=np.float32)
+            wpad[0, :, :cin] = hi.reshape(cout, cin, 9)
+            wpad[1, :, :cin] = lo.reshape(cout, cin, 9)
+            blob = np.zeros((chunks, nblk, 9, nt, 32, 4), dtype=np.float32)
+            lane = np.arange(32)
+            g, t = lane >> 2, lane & 3
+            for part in range(2):
+                for j in range(nt):
+                    for h in range(2):
+                        idx = part * 2 * nt + 2 * j + h
+                        for ch in range(chunks):
+                            for nb in range(nblk):
+                                n_idx = 8 * (nb * nt + j) + g                       # [32]
+                                c_idx = 8 * ch + t + 4 * h                           # [32]
+                                blob[ch, nb, :, idx // 4, :, idx % 4] = wpad[part, n_idx, c_idx, :].T   # [9, 32]
             assert blob.size == L.check(int(L.lib().kmsr_selector_weight_floats(cin, cout)))
             blobs.append((torch.from_numpy(blob.reshape(-1)).to(dev), torch.from_numpy(bf).to(dev)))
         self._cuda = (dev, blobs, self.fc_w.to(dev).contiguous(), self.fc_b.to(dev).contiguous())
