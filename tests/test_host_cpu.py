@@ -251,3 +251,46 @@ def test_selector_logits_match_the_reference_model(golden, synth):
     # the bank the reference model derives from its parameters is the shipped moe_kernels bank
     bank = golden("moe_bank.npz")
     assert np.abs(z["kernels"] - bank["kernels"]).max() <= 1e-8 and np.abs(z["sigmas"] - bank["sigmas"]).max() <= 2e-7
+
+
+def test_selector_weight_blobs_reproduce_the_reference_forward(golden):
+    """Host side of the learned kernel pick (selector.py, no GPU): BatchNorm folded into the convolutions, TF32 hi / lo
+    split (hi + lo equals the folded weight to 2^-22), fragment-major layout [chunk][block][tap][quad][lane][4].  The
+    blobs are read back exactly the way conv_mma_kernel's lanes index them (lane = (g, t), value index
+    part * 2 NT + 2 j + h <-> output channel 8 (block NT + j) + g, input channel 8 chunk + t + 4 h) and a float64
+    forward through them must give the logits of the torch fp32 forward and of the reference module."""
+    from kmsr_b200.selector import Selector
+    z = golden("selector.npz")
+    sel = Selector.from_npz(z, "cpu")
+    sel._prepare(torch.device("cpu"))
+    a = np.array([1.0, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -10, -3.1415926, 1e-30], dtype=np.float32)
+    t32 = Selector._tf32(a)
+    assert t32[0] == 1.0 and t32[1] == np.float32(1.0 + 2.0 ** -10) and t32[2] == a[2]       # ties away from zero
+    assert np.all((t32.view(np.uint32) & 0x1FFF) == 0) and np.abs(a - t32).max() <= 2.0 ** -10 * 3.2
+
+    def dense(blob, cin, cout):
+        nt = 8 if cout >= 64 else 4
+        chunks, nblk = (cin + 7) // 8, cout // (8 * nt)
+        b = blob.numpy().reshape(chunks, nblk, 9, nt, 32, 4).astype(np.float64)
+        w = np.zeros((cout, 8 * chunks, 9))
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            for part in range(2):
+                for j in range(nt):
+                    for h in range(2):
+                        idx = part * 2 * nt + 2 * j + h
+                        for nb in range(nblk):
+                            w[8 * (nb * nt + j) + g, t + 4 * h::8, :] += b[:, nb, :, idx // 4, lane, idx % 4]
+        assert np.abs(w[:, cin:]).max() == 0.0 if 8 * chunks > cin else True
+        return w[:, :cin].reshape(cout, cin, 3, 3)
+
+    rs = np.random.RandomState(4)
+    x = (rs.standard_normal((2, 5, 40, 56)) * 3.0 + 50.0).astype(np.float32)
+    h = torch.from_numpy(x).double()
+    for (blob, bias), (cin, cout) in zip(sel._cuda[1], ((5, 32), (32, 64), (64, 128))):
+        w = torch.from_numpy(dense(blob, cin, cout))
+        h = torch.relu(torch.nn.functional.conv2d(h, w, bias.double(), stride=2, padding=1))
+    lg = torch.nn.functional.linear(h.mean(dim=(2, 3)), sel.fc_w.double(), sel.fc_b.double()).numpy()
+    ref = sel.logits_library(torch.from_numpy(x)).numpy()
+    assert np.abs(lg - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.array_equal(lg.argmax(1), ref.argmax(1))
