@@ -68,8 +68,11 @@ enum {
                               H <= 512); KMSR_E_UNSUPPORTED if the shape does not qualify                      */
     KMSR_ALGO_STREAM = 3,  /* generic TMA row-streaming kernel (k in 11/13/15/21/31, factor 2/4/8, box mean,
                               W in 64/128/256*m); KMSR_E_UNSUPPORTED otherwise                             */
-    KMSR_ALGO_REG = 4      /* register-tile stencil kernel for the FP32-bound shapes (k in 11/13/15/21/31,
+    KMSR_ALGO_REG = 4,     /* register-tile stencil kernel for the FP32-bound shapes (k in 11/13/15/21/31,
                               factor 2/4, box mean, any H / W / strides); KMSR_E_UNSUPPORTED otherwise       */
+    KMSR_ALGO_BOX = 5      /* TMA box-tile register stencil (k in 11/13/15/21/31, factor 2/4/8, box mean, H % 8 == 0,
+                              W % 16 == 0, 16-byte aligned strides): the factor-2 / factor-4 sweep shapes and 64-wide
+                              patches; KMSR_E_UNSUPPORTED otherwise                                          */
 };
 
 /* ---- library ------------------------------------------------------------------------------- */
@@ -78,6 +81,11 @@ KMSR_API const char* kmsr_last_error(void);
 /* Device facts used to size grids / report rooflines (cudaGetDeviceProperties). */
 KMSR_API int kmsr_device_info(int device, int* sm_count, int* cc_major, int* cc_minor,
                               int64_t* l2_bytes, int64_t* smem_optin_bytes);
+/* Measurement aid (bench.py roofline.fp32_peak_tflops): one launch of dependent packed-FFMA2 chains on every SM of
+ * the current device, `iters` rounds; *fma_count (host) receives the fp32 multiply-adds the launch performs.  The
+ * caller times it with CUDA events on `stream`.  `sink` is a device buffer of >= 512 * sm_count floats (never
+ * written in practice).  Not part of the reference path.                                                        */
+KMSR_API int kmsr_fp32_probe(float* sink, int iters, double* fma_count, void* stream);
 
 /* ---- a2/a3: blur + downsample (+ noise) ------------------------------------------------------
  * Replaces apply_kernel_degradation (C_30:68-124 == C_31:59-97) for a batch of patches, the

@@ -20,16 +20,28 @@ BAND_NAMES = ["L_TOA_443", "L_TOA_490", "L_TOA_555", "L_TOA_660", "L_TOA_865"]  
 _pool_cache: dict = {}
 
 
+def _pool_checksum(arr: np.ndarray) -> tuple:
+    """Cheap content fingerprint: catches in-place edits of a pool that is still the same object."""
+    flat = arr.reshape(-1)
+    step = max(1, flat.size // 4096)
+    probe = np.ascontiguousarray(flat[::step][:4096])
+    return (float(probe.astype(np.float64).sum()), float(flat[-1]) if flat.size else 0.0)
+
+
 def _device_pool(noise_pool) -> torch.Tensor:
-    """Keep the last host pool resident on the device (it is replicated per GPU)."""
+    """Keep the last host pool resident on the device (it is replicated per GPU).  The cache holds a
+    reference to the source array and compares by identity (an address can be reused by a different pool once the
+    old one is freed) plus a sampled checksum (in-place edits)."""
     if isinstance(noise_pool, torch.Tensor) and noise_pool.is_cuda:
         return noise_pool
     arr = np.asarray(noise_pool)
-    key = (arr.__array_interface__["data"][0], arr.shape, str(arr.dtype), torch.cuda.current_device())
+    dev = torch.cuda.current_device()
     hit = _pool_cache.get("pool")
-    if hit is None or hit[0] != key:
-        _pool_cache["pool"] = (key, torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).cuda())
-    return _pool_cache["pool"][1]
+    chk = _pool_checksum(arr)
+    if hit is None or hit[0] is not arr or hit[1] != (arr.shape, str(arr.dtype), dev, chk):
+        _pool_cache["pool"] = (arr, (arr.shape, str(arr.dtype), dev, chk),
+                               torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).cuda())
+    return _pool_cache["pool"][2]
 
 
 def add_noise(blurred: np.ndarray, noise_pool: np.ndarray) -> np.ndarray:

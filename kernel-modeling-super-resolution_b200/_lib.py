@@ -12,13 +12,14 @@ LIB_PATH = os.path.join(_HERE, "libkmsr.so")
 PAD_REPLICATE, PAD_ZERO = 0, 1
 DOWN_BOXMEAN, DOWN_DECIMATE = 0, 1
 NOISE_NONE, NOISE_ADD, NOISE_SIGMA = 0, 1, 2
-ALGO_AUTO, ALGO_TILED, ALGO_TMA, ALGO_STREAM, ALGO_REG = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_TILED, ALGO_TMA, ALGO_STREAM, ALGO_REG, ALGO_BOX = 0, 1, 2, 3, 4, 5
 E_INVALID, E_UNSUPPORTED, E_CUDA, E_ALIGN = -1, -2, -3, -4
 
 PAD_MODES = {"replicate": PAD_REPLICATE, "zero": PAD_ZERO}
 DOWN_MODES = {"boxmean": DOWN_BOXMEAN, "decimate": DOWN_DECIMATE}
 NOISE_MODES = {"none": NOISE_NONE, "add": NOISE_ADD, "sigma": NOISE_SIGMA}
-ALGOS = {"auto": ALGO_AUTO, "tiled": ALGO_TILED, "tma": ALGO_TMA, "stream": ALGO_STREAM, "reg": ALGO_REG}
+ALGOS = {"auto": ALGO_AUTO, "tiled": ALGO_TILED, "tma": ALGO_TMA, "stream": ALGO_STREAM, "reg": ALGO_REG,
+         "box": ALGO_BOX}
 
 
 class KmsrError(RuntimeError):
@@ -37,6 +38,7 @@ SIGNATURES = {
     "kmsr_version": (_i32, []),
     "kmsr_last_error": (C.c_char_p, []),
     "kmsr_device_info": (_i32, [_i32, _pi, _pi, _pi, _pi64, _pi64]),
+    "kmsr_fp32_probe": (_i32, [_vp, _i32, C.POINTER(C.c_double), _vp]),
     "kmsr_degrade_out_size": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _pi, _pi]),
     "kmsr_composite_size": (_i32, [_i32, _i32, _i32, _i32, _pi, _pi, _pi]),
     "kmsr_degrade_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _i32, _i32]),

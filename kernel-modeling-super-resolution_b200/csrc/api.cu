@@ -39,6 +39,7 @@ int launch_estimate_sigma(const float*, long long, int, int, int, long long, dou
 int launch_nlm(const float*, long long, int, int, int, long long, const double*, const double*, double, int, float*,
                cudaStream_t);
 bool nlm_shape_ok(int, int, const char**);
+int launch_fp32_probe(float*, int, double*, cudaStream_t);
 long long selector_wsplit_floats(int, int);
 long long selector_workspace(long long, int, int);
 int launch_selector(const float*, long long, int, int, const float*, const float*, const float*, const float*, const float*,
@@ -65,6 +66,11 @@ KMSR_API int kmsr_device_info(int device, int* sm_count, int* cc_major, int* cc_
     if (l2_bytes) *l2_bytes = prop.l2CacheSize;
     if (smem_optin_bytes) *smem_optin_bytes = (int64_t)prop.sharedMemPerBlockOptin;
     return KMSR_OK;
+}
+
+KMSR_API int kmsr_fp32_probe(float* sink, int iters, double* fma_count, void* stream) {
+    KMSR_REQUIRE(sink != nullptr && iters >= 1, KMSR_E_INVALID, "fp32_probe: sink=%p iters=%d", (void*)sink, iters);
+    return launch_fp32_probe(sink, iters, fma_count, (cudaStream_t)stream);
 }
 
 KMSR_API int kmsr_degrade_out_size(int H, int W, int kh, int kw, int factor, int down_mode, int* Ho,
@@ -123,7 +129,7 @@ static int degrade_common(const float* hr, int64_t N, int C, int H, int W, int64
                  "degrade: pad_mode %d", pad_mode);
     KMSR_REQUIRE(noise_mode >= KMSR_NOISE_NONE && noise_mode <= KMSR_NOISE_SIGMA, KMSR_E_INVALID,
                  "degrade: noise_mode %d", noise_mode);
-    KMSR_REQUIRE(algo >= KMSR_ALGO_AUTO && algo <= KMSR_ALGO_REG, KMSR_E_INVALID, "degrade: algo %d", algo);
+    KMSR_REQUIRE(algo >= KMSR_ALGO_AUTO && algo <= KMSR_ALGO_BOX, KMSR_E_INVALID, "degrade: algo %d", algo);
     if (N == 0 || a.g.Ho == 0 || a.g.Wo == 0) return KMSR_OK;
     KMSR_REQUIRE(H >= 1 && W >= 1, KMSR_E_INVALID, "degrade: empty patch %dx%d", H, W);
     KMSR_REQUIRE(hr && comp && dsum && lr, KMSR_E_INVALID, "degrade: null pointer");
@@ -149,8 +155,19 @@ static int degrade_common(const float* hr, int64_t N, int C, int H, int W, int64
         return launch_degrade_tma(a, st);
     }
     if (algo == KMSR_ALGO_AUTO && tma_ok) return launch_degrade_tma(a, st);
+    // only the headline kernel writes the fused-statistics partials: nothing below may be handed a non-null stat_part
+    KMSR_REQUIRE(stat_part == nullptr, KMSR_E_UNSUPPORTED, "degrade: fused statistics need the TMA kernel (%s)", why);
+    const char* why4 = "";
+    const bool box_ok = box_shape_ok(a, down_mode, &why4);
+    if (algo == KMSR_ALGO_BOX) {
+        KMSR_REQUIRE(box_ok, KMSR_E_UNSUPPORTED, "degrade: box-tile kernel does not cover this call (%s)", why4);
+        return launch_degrade_box(a, st);
+    }
+    // factor 2 / 4 (FP32-bound or near the ridge) and 64-wide patches at any factor
+    if (algo == KMSR_ALGO_AUTO && box_ok && (a.g.stride <= 4 || (a.W <= 64 && a.H <= 64)) && a.W >= 48 && a.H >= 48)
+        return launch_degrade_box(a, st);
     const char* why3 = "";
-    const bool reg_ok = stat_part == nullptr && reg_shape_ok(a, down_mode, &why3);
+    const bool reg_ok = reg_shape_ok(a, down_mode, &why3);
     if (algo == KMSR_ALGO_REG) {
         KMSR_REQUIRE(reg_ok, KMSR_E_UNSUPPORTED, "degrade: register-tile kernel does not cover this call (%s)", why3);
         return launch_degrade_reg(a, st);
@@ -158,7 +175,7 @@ static int degrade_common(const float* hr, int64_t N, int C, int H, int W, int64
     // FP32-bound shapes: factor 2 (1.3-2.2x over the streaming kernel on every sweep cell), factor 4 on 64-wide patches
     if (algo == KMSR_ALGO_AUTO && reg_ok && (a.g.stride == 2 || a.W <= 64)) return launch_degrade_reg(a, st);
     const char* why2 = "";
-    const bool stream_ok = stat_part == nullptr && stream_shape_ok(a, down_mode, &why2);
+    const bool stream_ok = stream_shape_ok(a, down_mode, &why2);
     if (algo == KMSR_ALGO_STREAM) {
         KMSR_REQUIRE(stream_ok, KMSR_E_UNSUPPORTED, "degrade: streaming kernel does not cover this call (%s)", why2);
         return launch_degrade_stream(a, st);
@@ -218,13 +235,14 @@ KMSR_API int kmsr_degrade_stats_prepared(const float* hr, int64_t N, int C, int 
                  "degrade_stats: workspace of %lld B needed, %lld given", (long long)need, (long long)workspace_bytes);
     double* part = (double*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     // fused when the TMA kernel takes the call, otherwise the two kernels run back to back (same results contract)
-    DegradeArgs probe;
+    DegradeArgs probe{};
+    probe.stat_part = part;
     int rc = make_geometry(H, W, kh, kw, factor, down_mode, &probe.g);
     KMSR_REQUIRE(rc == KMSR_OK, rc, "degrade_stats: bad geometry");
     probe.hr = hr; probe.N = N; probe.C = C; probe.H = H; probe.W = W; probe.sN = hr_stride_n; probe.sC = hw; probe.sH = W;
     probe.patch_offsets = nullptr; probe.scene_h = probe.scene_w = 0; probe.x_multiple = 1; probe.pad_mode = pad_mode;
     const char* why = "";
-    const bool fused = algo != KMSR_ALGO_TILED && N > 0 && tma_shape_ok(probe, &why);
+    const bool fused = (algo == KMSR_ALGO_AUTO || algo == KMSR_ALGO_TMA) && N > 0 && tma_shape_ok(probe, &why);
     rc = degrade_common(hr, N, C, H, W, hr_stride_n, hw, W, nullptr, 0, 0, 1, comp, dsum, nK, kh, kw, kidx, sigma, pool,
                         nPool, nidx, factor, pad_mode, down_mode, noise_mode, lr, algo, stream, fused ? part : nullptr);
     if (rc != KMSR_OK || N == 0) return rc;

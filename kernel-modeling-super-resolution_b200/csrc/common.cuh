@@ -112,5 +112,7 @@ bool stream_shape_ok(const DegradeArgs& a, int down_mode, const char** why);
 int launch_degrade_stream(const DegradeArgs& a, cudaStream_t st);
 bool reg_shape_ok(const DegradeArgs& a, int down_mode, const char** why);
 int launch_degrade_reg(const DegradeArgs& a, cudaStream_t st);
+bool box_shape_ok(const DegradeArgs& a, int down_mode, const char** why);
+int launch_degrade_box(const DegradeArgs& a, cudaStream_t st);
 
 }  // namespace kmsr

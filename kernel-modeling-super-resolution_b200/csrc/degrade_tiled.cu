@@ -137,7 +137,9 @@ degrade_tiled_kernel(const TiledParams p) {
             for (int j = 0; j < 4; ++j) {
                 int t, m;
                 split_col<S_>(4 * v4 + j, S, t, m);
-                d[j] = trow[t * p.PM + m];
+                // taps KW .. KWp-1 are row padding (weight 0): they must not meet the neighbouring window's pixels, or a
+                // NaN / Inf up to three columns right of an output's window would poison it (0 * NaN)
+                d[j] = 4 * v4 + j < p.KW ? trow[t * p.PM + m] : 0.0f;
             }
 #pragma unroll
             for (int ty = 0; ty < TY; ++ty) {

@@ -48,10 +48,14 @@ class PairSynthesizer:
                                  factor=self.factor, pad_mode=self.pad_mode, down_mode=self.down_mode,
                                  noise_mode=self.noise_mode, out=out, algo=self.algo)
 
-    def run_host(self, hr_host: torch.Tensor, kidx=None, nidx=None, lr_host: torch.Tensor | None = None) -> torch.Tensor:
+    def run_host(self, hr_host: torch.Tensor, kidx=None, nidx=None, lr_host: torch.Tensor | None = None,
+                 sync: bool = True) -> torch.Tensor:
         """hr_host: CPU float32 [N,C,H,W] (pinned for full-speed copies) -> lr_host CPU [N,C,Ho,Wo].
 
         Double-buffered: H2D of chunk i+1 overlaps the kernel on chunk i and the D2H of chunk i-1.
+        With `sync` (default) the call returns once the last device-to-host copy has landed, so the returned CPU
+        tensor can be read right away; `sync=False` returns while copies may still be in flight (the current stream
+        has been made to wait for them: synchronise it, or the device, before touching `lr_host`).
         """
         from . import _lib as L
         n, c, h, w = hr_host.shape
@@ -90,6 +94,8 @@ class PairSynthesizer:
                 lr_host[a:b].copy_(outs[s][:b - a], non_blocking=True)
                 out_free[s].record(self._out)
         main.wait_stream(self._out)
+        if sync:
+            self._out.synchronize()
         return lr_host
 
 
@@ -102,5 +108,4 @@ def synthesize_pairs(hr, kernel_bank, sigma_bank, noise_pool, seed: int = 42, fa
     if t.is_cuda:
         return syn.run_device(t, kidx, nidx), kidx, nidx
     lr = syn.run_host(t, kidx, nidx)
-    torch.cuda.current_stream().synchronize()
     return lr, kidx, nidx

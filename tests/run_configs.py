@@ -331,10 +331,17 @@ def config5(args, rank, world, dev):
                 pb = ops.prepare_kernels(kern, s)
                 ho = p // s
                 out = torch.empty((n, C, ho, ho), device=dev)
-                ms = timed(lambda: ops.degrade_batch(hr, pb, factor=s, out=out), 2, 1)
+                ms = timed(lambda: ops.degrade_batch(hr, pb, factor=s, out=out), args.reps, 1)
+                auto_algo = _lib.last_algo()
+                alts = {}
+                for alg in [x for x in args.c5_algos.split(",") if x and x != auto_algo]:
+                    try:
+                        alts[alg] = timed(lambda: ops.degrade_batch(hr, pb, factor=s, out=out, algo=alg), args.reps, 1)
+                    except Exception:
+                        pass                                   # the kernel does not take this shape
                 by = 4 * C * (p * p + ho * ho) * n
                 fma = C * ho * ho * (k + s - 1) ** 2 * n
-                rows.append({"k": k, "P": p, "s": s, "n": n, "algo": _lib.last_algo(), "ms": ms,
+                rows.append({"k": k, "P": p, "s": s, "n": n, "algo": auto_algo, "ms": ms, "alt_ms": alts,
                              "pairs_per_s": n / (ms * 1e-3), "gbs": by / (ms * 1e-3) / 1e9,
                              "hbm_frac": by / (ms * 1e-3) / 1e9 / HBM_PEAK, "tflops": 2 * fma / (ms * 1e-3) / 1e12,
                              "fp32_frac": 2 * fma / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
@@ -365,6 +372,7 @@ def main():
     ap.add_argument("--c3-check", type=int, default=2048)
     ap.add_argument("--c4-size", type=int, default=8192)
     ap.add_argument("--c5-gb", type=float, default=4.0)
+    ap.add_argument("--c5-algos", default="", help="config 5: also time these kernels (comma list of box,reg,stream,tma)")
     args = ap.parse_args()
     assert torch.cuda.is_available(), "needs a CUDA device; there is no CPU fallback"
     rank, local, world = shard.init_distributed()

@@ -346,6 +346,41 @@ def test_generic_streaming_kernel(K, synth, k, s, p):
 def test_register_tile_kernel(K, synth, k, s, h, w):
     """degrade_reg<K, S> (the FP32-bound shapes of BASELINE config 5; any H / W, partial tiles, narrow groups):
     replicate and zero padding, noise epilogue, NaN footprint, strided views, against the reference call sites."""
+    _check_stencil_kernel(K, synth, "reg", k, s, h, w)
+
+
+@pytest.mark.parametrize("k,s,h,w", [(11, 2, 64, 64), (13, 2, 128, 128), (15, 4, 256, 256), (21, 2, 256, 256), (31, 4, 128, 128),
+                                     (31, 2, 64, 64), (21, 4, 512, 512), (11, 4, 64, 64), (13, 2, 72, 208), (15, 2, 136, 80),
+                                     (31, 2, 40, 304), (13, 4, 104, 48), (13, 8, 64, 64), (31, 8, 64, 64), (15, 8, 128, 128),
+                                     (21, 8, 64, 64), (11, 8, 56, 48), (13, 4, 64, 64), (15, 4, 64, 64), (21, 4, 64, 64)])
+def test_box_tile_kernel(K, synth, k, s, h, w):
+    """degrade_box<K, S> (TMA box tiles: factor 2 / 4 sweep shapes, 64-wide patches at any factor; partial tiles,
+    whole-band-per-warp mode, strided views): same checks as the register-tile kernel."""
+    _check_stencil_kernel(K, synth, "box", k, s, h, w)
+
+
+def test_box_tile_kernel_multi_kernel_noise(K, synth):
+    """kidx / nidx / sigma through the box kernel (tile mode and band mode) against the tiled kernel and the oracle."""
+    for (k, s, p, n) in ((13, 4, 128, 7), (11, 2, 64, 9), (21, 2, 256, 3)):
+        bank = np.stack([synth.softmax_kernels(k, 50 + i) for i in range(4)])
+        sig = np.linspace(0.5, 1.2, 4 * 5, dtype=np.float32).reshape(4, 5)
+        hr = synth.make_hr(n, 4100 + k, "textured", size=p)
+        ho = p // s
+        pool = (np.random.RandomState(11).standard_normal((6, 5, ho, ho)) * 0.5).astype(np.float32)
+        kidx = np.random.RandomState(12).randint(0, 4, n).astype(np.int32)
+        nidx = np.random.RandomState(13).randint(0, 6, n).astype(np.int32)
+        hd, kd = torch.from_numpy(hr).cuda(), torch.from_numpy(bank).cuda()
+        lb = K.ops.degrade_batch(hd, kd, kidx=kidx, sigma=torch.from_numpy(sig), pool=torch.from_numpy(pool).cuda(),
+                                 nidx=nidx, factor=s, noise_mode="sigma", algo="box").cpu().numpy()
+        assert K.lib.last_algo() == "box"
+        for i in range(n):
+            ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(bank[kidx[i]]), s).numpy()
+            nz = sig[kidx[i]][:, None, None].astype(np.float64) * pool[nidx[i]]
+            ref = (ref + (sig[kidx[i]][:, None, None] * pool[nidx[i]]).astype(np.float32)).astype(np.float32)
+            check_pixels(lb[i], ref, hr[i], exact_degrade(hr[i], bank[kidx[i]], s), noise=nz, name=f"box multi k{k} s{s} #{i}")
+
+
+def _check_stencil_kernel(K, synth, algo, k, s, h, w):
     n = 3
     kern = synth.softmax_kernels(k, 7 + k)
     p = max(h, w)
@@ -354,18 +389,18 @@ def test_register_tile_kernel(K, synth, k, s, h, w):
     hr = np.ascontiguousarray(full[:, :, :h, :w])
     hd = torch.from_numpy(full).cuda()[:, :, :h, :w]           # a strided view: rows contiguous, row stride p
     kd = torch.from_numpy(kern).cuda()
-    lr = K.ops.degrade_batch(hd, kd, factor=s, algo="reg").cpu().numpy()
-    assert K.lib.last_algo() == "reg" and lr.shape == (n, 5, h // s, w // s)
+    lr = K.ops.degrade_batch(hd, kd, factor=s, algo=algo).cpu().numpy()
+    assert K.lib.last_algo() == algo and lr.shape == (n, 5, h // s, w // s)
     for i in range(n):
         ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kern), s).numpy()
-        check_pixels(lr[i], ref, hr[i], exact_degrade(hr[i], kern, s), name=f"reg k{k} s{s} {h}x{w} #{i}")
+        check_pixels(lr[i], ref, hr[i], exact_degrade(hr[i], kern, s), name=f"{algo} k{k} s{s} {h}x{w} #{i}")
     # zero padding (train_gemini.py:128) + sigma noise: held to the exact (fp64) value
     ho, wo = h // s, w // s
     pool = (np.random.RandomState(3).standard_normal((5, 5, ho, wo)) * 0.5).astype(np.float32)
     sig = np.linspace(0.7, 1.0, 5, dtype=np.float32)[None]
     nidx = np.array([4, 0, 2], dtype=np.int32)
     lz = K.ops.degrade_batch(hd, kd, factor=s, pad_mode="zero", sigma=torch.from_numpy(sig), pool=torch.from_numpy(pool).cuda(),
-                             nidx=nidx, noise_mode="sigma", algo="reg").cpu().numpy()
+                             nidx=nidx, noise_mode="sigma", algo=algo).cpu().numpy()
     for i in range(n):
         rngs = orc.band_range(hr[i])
         ex = exact_degrade(hr[i], kern, s, zero_pad=True) + sig[0][:, None, None].astype(np.float64) * pool[nidx[i]]
@@ -377,7 +412,7 @@ def test_register_tile_kernel(K, synth, k, s, h, w):
     hn[0, 1, 0, 0] = np.nan
     hn[1, 3, h // 2, w // 3] = np.nan
     hn[2, 0, h - 1, w - 1] = np.nan
-    ln = K.ops.degrade_batch(torch.from_numpy(hn).cuda(), kd, factor=s, algo="reg").cpu().numpy()
+    ln = K.ops.degrade_batch(torch.from_numpy(hn).cuda(), kd, factor=s, algo=algo).cpu().numpy()
     for i in range(n):
         ref = orc.apply_kernel_degradation(torch.from_numpy(hn[i]), torch.from_numpy(kern), s).numpy()
         assert np.array_equal(np.isnan(ln[i]), np.isnan(ref)), (k, s, h, w, i)
