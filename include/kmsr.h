@@ -87,6 +87,15 @@ KMSR_API int kmsr_device_info(int device, int* sm_count, int* cc_major, int* cc_
  * written in practice).  Not part of the reference path.                                                        */
 KMSR_API int kmsr_fp32_probe(float* sink, int iters, double* fma_count, void* stream);
 
+/* Opt-in range check for DEVICE-resident int32 indices (kidx < nK, nidx < nPool, crop offsets): the degrade / gather
+ * kernels trust their indices (an index >= nK / nPool is an out-of-bounds device read).  Host-side callers check host
+ * arrays for free (ops.py does); for arrays that only exist on the device this entry counts the entries outside
+ * [0, upper) on `stream`, SYNCHRONISES it, and returns KMSR_E_INVALID (message names `what` and the count) if any.
+ * `scratch` is one caller-owned device int32.  Mirrors the reference's IndexError on noise_pool[idx]
+ * (E_make_train_data.py:72-74) and its crop contract (D_build_noise_pool.py:44-45).                              */
+KMSR_API int kmsr_validate_indices(const int32_t* idx, int64_t n, int64_t upper, int32_t* scratch,
+                                   const char* what, void* stream);
+
 /* ---- a2/a3: blur + downsample (+ noise) ------------------------------------------------------
  * Replaces apply_kernel_degradation (C_30:68-124 == C_31:59-97) for a batch of patches, the
  * multi-kernel + sigma composition of SURVEY.md 8a row 3 (train_gemini.py:107-138) and the

@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkmsr.so")
+# KMSR_LIB selects another build of the same library (libkmsr_debug.so: device-side asserts; libkmsr_bench.so:
+# measurement switches) -- never a different implementation
+LIB_PATH = os.environ.get("KMSR_LIB") or os.path.join(_HERE, "libkmsr.so")
 
 # enums of include/kmsr.h
 PAD_REPLICATE, PAD_ZERO = 0, 1
@@ -38,6 +40,7 @@ SIGNATURES = {
     "kmsr_version": (_i32, []),
     "kmsr_last_error": (C.c_char_p, []),
     "kmsr_device_info": (_i32, [_i32, _pi, _pi, _pi, _pi64, _pi64]),
+    "kmsr_validate_indices": (_i32, [_vp, _i64, _i64, _vp, C.c_char_p, _vp]),
     "kmsr_fp32_probe": (_i32, [_vp, _i32, C.POINTER(C.c_double), _vp]),
     "kmsr_degrade_out_size": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _pi, _pi]),
     "kmsr_composite_size": (_i32, [_i32, _i32, _i32, _i32, _pi, _pi, _pi]),

@@ -40,6 +40,7 @@ int launch_nlm(const float*, long long, int, int, int, long long, const double*,
                cudaStream_t);
 bool nlm_shape_ok(int, int, const char**);
 int launch_fp32_probe(float*, int, double*, cudaStream_t);
+int launch_validate_indices(const int*, long long, long long, int*, int*, cudaStream_t);
 long long selector_wsplit_floats(int, int);
 long long selector_workspace(long long, int, int);
 int launch_selector(const float*, long long, int, int, const float*, const float*, const float*, const float*, const float*,
@@ -71,6 +72,19 @@ KMSR_API int kmsr_device_info(int device, int* sm_count, int* cc_major, int* cc_
 KMSR_API int kmsr_fp32_probe(float* sink, int iters, double* fma_count, void* stream) {
     KMSR_REQUIRE(sink != nullptr && iters >= 1, KMSR_E_INVALID, "fp32_probe: sink=%p iters=%d", (void*)sink, iters);
     return launch_fp32_probe(sink, iters, fma_count, (cudaStream_t)stream);
+}
+
+KMSR_API int kmsr_validate_indices(const int32_t* idx, int64_t n, int64_t upper, int32_t* scratch, const char* what,
+                                   void* stream) {
+    KMSR_REQUIRE(n >= 0 && upper >= 0, KMSR_E_INVALID, "validate_indices: n=%lld upper=%lld", (long long)n, (long long)upper);
+    if (n == 0) return KMSR_OK;
+    KMSR_REQUIRE(idx && scratch, KMSR_E_INVALID, "validate_indices: null pointer");
+    int bad = 0;
+    int rc = launch_validate_indices(idx, n, upper, scratch, &bad, (cudaStream_t)stream);
+    if (rc != KMSR_OK) return rc;
+    KMSR_REQUIRE(bad == 0, KMSR_E_INVALID, "%s: %d of %lld indices lie outside [0, %lld)", what ? what : "indices", bad,
+                 (long long)n, (long long)upper);
+    return KMSR_OK;
 }
 
 KMSR_API int kmsr_degrade_out_size(int H, int W, int kh, int kw, int factor, int down_mode, int* Ho,

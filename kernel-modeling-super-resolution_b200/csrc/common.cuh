@@ -7,6 +7,16 @@
 
 #include "../../include/kmsr.h"
 
+// Debug build (make DEBUG=1 -> libkmsr_debug.so, -DKMSR_DEBUG_ASSERTS): device-side asserts on ring slots, staged rows
+// and noise-tile indices of the TMA kernels.  compute-sanitizer is closed on this pool; the GPU parity suite is run once
+// per round against this library instead (KMSR_LIB=.../libkmsr_debug.so).  The release build compiles them away.
+#ifdef KMSR_DEBUG_ASSERTS
+#include <assert.h>
+#define KMSR_DASSERT(cond) assert(cond)
+#else
+#define KMSR_DASSERT(cond) ((void)0)
+#endif
+
 namespace kmsr {
 
 void set_error(const char* fmt, ...);

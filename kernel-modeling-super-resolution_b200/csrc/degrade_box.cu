@@ -144,14 +144,25 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
             tma_load_5d(smem_u32(region + (size_t)lane * a.planeF), &tmap, rx0, lane, ry0 / 8, c, (int)n, bar);
     }
 
-    // ---- per-band parameters and the composite kernel (shifted by one float when the first tap is odd) ----
+    // ---- per-band parameters and the composite kernel (shifted by one float when the first tap is odd): cp.async, so
+    // one global-memory latency covers the whole copy (register-returning loads made a lone warp pay it per element)
     const int kid = a.kidx ? __ldg(a.kidx + n) : 0;
     {
         const float* kc = a.comp + ((long long)kid * a.C + c) * (G::KW * a.KWp);
-        for (int d = gtid; d < G::KW * G::WP; d += gthreads) {
-            const int u = d / G::WP, v = d - u * G::WP - G::ODD;
-            wsm[d] = (v >= 0 && v < G::KW) ? __ldg(kc + u * a.KWp + v) : 0.0f;
+        const uint32_t wdst = smem_u32(wsm);
+        if (!G::ODD && a.KWp == G::WP) {
+            for (int e = gtid; e < G::KW * G::WP / 4; e += gthreads)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wdst + 16 * e), "l"(kc + 4 * e) : "memory");
+        } else {
+            for (int d = gtid; d < G::KW * G::WP; d += gthreads) {
+                const int u = d / G::WP, v = d - u * G::WP - G::ODD;
+                if (v >= 0 && v < G::KW)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(wdst + 4 * d), "l"(kc + u * a.KWp + v) : "memory");
+                else
+                    wsm[d] = 0.0f;
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     const bool noisy = a.noise_mode != KMSR_NOISE_NONE;
     const float ds = __ldg(a.dsum + (long long)kid * a.C + c);
@@ -166,8 +177,11 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
     const bool replicate = a.replicate != 0;
     const bool ledge = replicate && tileX0 + 16 * lx == 0;        // halo columns left of the band in this thread's segment
     const bool redge = replicate && colsLeft == 16;               // ... right of the band (W % 16 == 0: box_shape_ok)
+    // warp-uniform guards: only warps that hold an edge thread issue the substitution moves at all
+    const bool wledge = __any_sync(0xffffffffu, ledge), wredge = __any_sync(0xffffffffu, redge);
     const float* tbase = region + 16 * lx;
 
+    asm volatile("cp.async.wait_all;" ::: "memory");
     if (BAND) __syncwarp();
     else __syncthreads();                                         // composite kernel staged
     mbar_wait(bar, 0);
@@ -196,6 +210,7 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
         const int hr_row = hy0 + rr;
         const int cl_row = min(max(hr_row, 0), a.H - 1);
         const int t = ((replicate || BAND) ? cl_row : hr_row) - ry0;
+        KMSR_DASSERT(t >= 0 && t < 8 * a.NQ && 16 * lx + 4 * G::NL4 <= a.WB);     // the segment lies inside the staged region
         const ulonglong2* prow = reinterpret_cast<const ulonglong2*>(tbase + (size_t)(t & 7) * a.planeF + (t >> 3) * a.WB);
 #pragma unroll
         for (int i = 0; i < G::NL4; ++i) {
@@ -206,17 +221,17 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
 #pragma unroll
             for (int i = 0; i < G::NPL; ++i) P[i] = 0ull;
         }
-        if (ledge) {
+        if (wledge) {
             const float v = lo2(P[G::PADL / 2]);
             const u64 vv = pack2(v, v);
 #pragma unroll
-            for (int i = 0; i < G::PADL / 2; ++i) P[i] = vv;
+            for (int i = 0; i < G::PADL / 2; ++i) P[i] = ledge ? vv : P[i];
         }
-        if (redge) {
+        if (wredge) {
             const float v = hi2(P[G::RPAIR - 1]);
             const u64 vv = pack2(v, v);
 #pragma unroll
-            for (int i = G::RPAIR; i < G::NPL; ++i) P[i] = vv;
+            for (int i = G::RPAIR; i < G::NPL; ++i) P[i] = redge ? vv : P[i];
         }
 #pragma unroll
         for (int i = 0; i < G::NPL; ++i) P[i] = add2(P[i], npv2);

@@ -53,6 +53,31 @@ crop_sub_kernel(const float* __restrict__ geo, const float* __restrict__ den, in
     }
 }
 
+// counts the entries of idx outside [0, upper): the opt-in range check for device-resident indices
+__global__ void __launch_bounds__(256)
+count_out_of_range_kernel(const int* __restrict__ idx, long long n, long long upper, int* __restrict__ bad) {
+    int mine = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = idx[i];
+        mine += (v < 0 || v >= upper) ? 1 : 0;
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(bad, mine);
+}
+
+int launch_validate_indices(const int* idx, long long n, long long upper, int* bad, int* bad_host, cudaStream_t st) {
+    *bad_host = 0;
+    if (n == 0) return KMSR_OK;
+    KMSR_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+    long long blocks = (n + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    count_out_of_range_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, n, upper, bad);
+    KMSR_LAUNCH_CHECK("count_out_of_range_kernel");
+    KMSR_CUDA_OK(cudaMemcpyAsync(bad_host, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    KMSR_CUDA_OK(cudaStreamSynchronize(st));
+    return KMSR_OK;
+}
+
 int launch_add_noise(const float* blurred, long long N, int C, long long hw, const float* pool,
                      const int* nidx, const float* sigma, const int* kidx, float* out,
                      cudaStream_t st) {

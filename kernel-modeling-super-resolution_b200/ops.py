@@ -41,6 +41,33 @@ def _i32(t, device) -> torch.Tensor | None:
     return t.to(device=device, dtype=torch.int32).contiguous()
 
 
+def _check_indices(what: str, idx, n: int, upper: int, device, validate_device: bool = False) -> None:
+    """kidx < nK, nidx < nPool, crop offsets: a bad index is an out-of-bounds device read in the kernels, so host arrays
+    are range-checked here for free (IndexError, as noise_pool[idx] raises in the reference, E:72-74) and device tensors
+    through kmsr_validate_indices when the caller opts in (`validate=True`; it synchronises the stream)."""
+    if idx is None:
+        return
+    count = int(idx.numel()) if isinstance(idx, torch.Tensor) else int(np.asarray(idx).size)
+    if count != n:
+        raise ValueError(f"{what}: {count} indices for {n} patches")
+    if n == 0:
+        return
+    if isinstance(idx, torch.Tensor) and idx.is_cuda:
+        if validate_device:
+            t = idx.to(torch.int32).contiguous()
+            scratch = torch.zeros(1, dtype=torch.int32, device=t.device)
+            with torch.cuda.device(t.device):
+                rc = L.lib().kmsr_validate_indices(_ptr(t), n, int(upper), _ptr(scratch), what.encode(), _stream(t.device))
+            if rc == L.E_INVALID:
+                raise IndexError(L.last_error())
+            L.check(rc)
+        return
+    a = idx.numpy() if isinstance(idx, torch.Tensor) else np.asarray(idx)
+    lo, hi = int(a.min()), int(a.max())
+    if lo < 0 or hi >= upper:
+        raise IndexError(f"{what}: values span [{lo}, {hi}], valid range is [0, {upper})")
+
+
 @dataclass
 class PreparedBank:
     """Normalised + box-folded kernel bank on the device (kmsr_prepare_kernels)."""
@@ -79,7 +106,7 @@ def degrade_batch(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, 
                   noise_mode: str | None = None, out: torch.Tensor | None = None, algo: str = "auto",
                   patch_offsets: torch.Tensor | None = None, patch_hw: tuple[int, int] | None = None,
                   strides: tuple[int, int, int] | None = None, n_patches: int | None = None,
-                  scene_hw: tuple[int, int] | None = None, x_multiple: int = 1) -> torch.Tensor:
+                  scene_hw: tuple[int, int] | None = None, x_multiple: int = 1, validate: bool = False) -> torch.Tensor:
     """lr[n,c] = degrade(hr[n], K[kidx[n]])[c] (+ scale * pool[nidx[n], c]) on the device.
 
     hr: CUDA float32 [N, C, H, W] with contiguous rows (any N / C / row strides), or -- with
@@ -123,19 +150,10 @@ def degrade_batch(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, 
         out = torch.empty((N, Cc, Ho, Wo), dtype=torch.float32, device=dev)
     else:
         assert out.is_cuda and out.is_contiguous() and tuple(out.shape) == (N, Cc, Ho, Wo)
+    _check_indices("kidx", kidx, N, bank.nK, dev, validate)
     kidx_d = _i32(kidx, dev)
     nidx_d = _i32(nidx, dev)
-    sig = None if sigma is None else _f32(torch.as_tensor(sigma), dev).contiguous()
-    pl = None
-    npool = 0
-    if nm != L.NOISE_NONE:
-        if pool is None or nidx_d is None:
-            raise ValueError("noise requested without pool / nidx")
-        pl = pool if (pool.is_cuda and pool.dtype == torch.float32 and pool.is_contiguous()) \
-            else _f32(pool, dev).contiguous()
-        npool = pl.shape[0]
-        if tuple(pl.shape[1:]) != (Cc, Ho, Wo):
-            raise ValueError(f"noise pool {tuple(pl.shape)} does not match LR patches {(Cc, Ho, Wo)}")
+    sig, pl, npool = _noise_args(nm, sigma, pool, nidx, N, bank, (Cc, Ho, Wo), dev, validate)
     if po is not None and scene_hw is not None:
         with torch.cuda.device(dev):
             L.check(L.lib().kmsr_degrade_windows(
@@ -153,9 +171,29 @@ def degrade_batch(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, 
     return out
 
 
+def _noise_args(nm, sigma, pool, nidx, N, bank, lr_shape, dev, validate):
+    """sigma [nK,C], pool [nPool,C,Ho,Wo] and the nidx range, validated once for degrade_batch and degrade_batch_stats."""
+    sig = None if sigma is None else _f32(torch.as_tensor(sigma), dev).contiguous()
+    if nm == L.NOISE_NONE:
+        return sig, None, 0
+    if pool is None or nidx is None:
+        raise ValueError("noise requested without pool / nidx")
+    pl = pool if (pool.is_cuda and pool.dtype == torch.float32 and pool.is_contiguous()) else _f32(pool, dev).contiguous()
+    if pl.ndim != 4 or tuple(pl.shape[1:]) != tuple(lr_shape):
+        raise ValueError(f"noise pool {tuple(pl.shape)} does not match LR patches {tuple(lr_shape)}")
+    if nm == L.NOISE_SIGMA:
+        if sig is None:
+            raise ValueError("noise_mode 'sigma' without sigma")
+        if tuple(sig.shape) != (bank.nK, bank.C):
+            raise ValueError(f"sigma {tuple(sig.shape)} does not match the kernel bank {(bank.nK, bank.C)}")
+    _check_indices("nidx", nidx, N, int(pl.shape[0]), dev, validate)
+    return sig, pl, int(pl.shape[0])
+
+
 def degrade_batch_stats(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=None, nidx=None, factor: int = 8,
                         pad_mode: str = "replicate", down_mode: str = "boxmean", noise_mode: str | None = None,
-                        out: torch.Tensor | None = None, sums: torch.Tensor | None = None, algo: str = "auto"):
+                        out: torch.Tensor | None = None, sums: torch.Tensor | None = None, algo: str = "auto",
+                        validate: bool = False):
     """degrade_batch + band_stats of the HR patches in one pass (E_make_train_data.py:223-250 with
     data_mean_std.py:32-33 fused): returns (lr, mean [N,C] f64, std [N,C] f64); `sums` (f64 [2C+1]) is
     accumulated as in band_stats.  hr: contiguous CUDA float32 [N, C, H, W]."""
@@ -177,14 +215,14 @@ def degrade_batch_stats(hr: torch.Tensor, kbank, *, kidx=None, sigma=None, pool=
     Ho, Wo = L.degrade_out_size(H, W, bank.kh, bank.kw, factor, dm)
     if out is None:
         out = torch.empty((N, Cc, Ho, Wo), dtype=torch.float32, device=dev)
+    elif not (out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (N, Cc, Ho, Wo)):
+        raise ValueError(f"out must be a contiguous CUDA float32 tensor {(N, Cc, Ho, Wo)}")
+    if sums is not None and not (sums.is_cuda and sums.is_contiguous() and sums.dtype == torch.float64
+                                 and sums.numel() == 2 * Cc + 1):
+        raise ValueError(f"sums must be a contiguous CUDA float64 tensor of {2 * Cc + 1} elements")
+    _check_indices("kidx", kidx, N, bank.nK, dev, validate)
     kidx_d, nidx_d = _i32(kidx, dev), _i32(nidx, dev)
-    sig = None if sigma is None else _f32(torch.as_tensor(sigma), dev).contiguous()
-    pl, npool = None, 0
-    if nm != L.NOISE_NONE:
-        if pool is None or nidx_d is None:
-            raise ValueError("noise requested without pool / nidx")
-        pl = pool if (pool.is_cuda and pool.dtype == torch.float32 and pool.is_contiguous()) else _f32(pool, dev).contiguous()
-        npool = pl.shape[0]
+    sig, pl, npool = _noise_args(nm, sigma, pool, nidx, N, bank, (Cc, Ho, Wo), dev, validate)
     mean = torch.empty((N, Cc), dtype=torch.float64, device=dev)
     std = torch.empty((N, Cc), dtype=torch.float64, device=dev)
     wsb = int(L.check(L.lib().kmsr_degrade_stats_workspace_bytes(N, Cc)))
@@ -213,6 +251,9 @@ def add_noise_batch(blurred: torch.Tensor, pool: torch.Tensor, nidx, *, sigma=No
     if out is None:
         out = torch.empty_like(b)
     sig = None if sigma is None else _f32(torch.as_tensor(sigma), dev).contiguous()
+    _check_indices("nidx", nidx, N, int(pl.shape[0]), dev)
+    if sig is not None:
+        _check_indices("kidx", kidx, N, int(sig.shape[0]), dev)
     with torch.cuda.device(dev):
         L.check(L.lib().kmsr_add_noise(_ptr(b), N, Cc, hw, _ptr(pl), pl.shape[0], _ptr(_i32(nidx, dev)),
                                        _ptr(sig), _ptr(_i32(kidx, dev)), _ptr(out), _stream(dev)))
@@ -223,11 +264,23 @@ def crop_sub(geo: torch.Tensor, den: torch.Tensor, top, left, crop: int) -> torc
     """pool[m] = (geo - den)[:, top[m]:top[m]+crop, left[m]:left[m]+crop]  (D_build_noise_pool.py:88, :51)."""
     require_cuda()
     dev = geo.device
+    if geo.ndim != 3 or tuple(den.shape) != tuple(geo.shape):
+        # the reference's `geo - den` (D:88) raises on a shape mismatch before any crop offset is drawn
+        raise ValueError(f"geophysical_data {tuple(geo.shape)} and denoised {tuple(den.shape)} must be the same [C,H,W]")
+    if geo.dtype != torch.float32 or den.dtype != torch.float32:
+        raise TypeError("crop_sub expects float32 tensors")
     g = geo.contiguous()
     d = den.to(dev).contiguous()
     Cc, H, W = g.shape
-    t = _i32(np.asarray(top), dev)
-    l = _i32(np.asarray(left), dev)
+    if crop > H or crop > W:
+        raise ValueError(f"crop {crop} is larger than the image {H}x{W}")          # D:44-45
+    ta, la = np.asarray(top), np.asarray(left)
+    if ta.shape != la.shape:
+        raise ValueError("top / left must have the same length")
+    _check_indices("crop top", ta, int(ta.size), H - crop + 1, dev)
+    _check_indices("crop left", la, int(la.size), W - crop + 1, dev)
+    t = _i32(ta, dev)
+    l = _i32(la, dev)
     n = int(t.numel())
     out = torch.empty((n, Cc, crop, crop), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -356,3 +409,39 @@ def denoise_nlm(x: torch.Tensor, h_factor: float = 1.15, patch_size: int = 7, pa
         L.check(L.lib().kmsr_denoise_nlm(_ptr(x), N, Cc, H, W, sn, float(h_factor), int(patch_size), int(patch_distance),
                                          _ptr(out), _ptr(sigma), _ptr(ws), wsb, _stream(dev)))
     return out, sigma
+
+
+def fp32_peak_tflops(device=None, sustained_ms: float = 150.0) -> dict:
+    """What this device does in packed FFMA2 (kmsr_fp32_probe), in TFLOP/s (2 flops per multiply-add): the FP32-FMA
+    roofline denominator.  {"burst": best of several ~2 ms launches with pauses between them -- the figure for a kernel
+    timed alone --, "sustained": one launch of ~sustained_ms, where the 1 kW power cap has pulled the SM clock down --
+    the figure for a kernel inside a long step}.  A measurement aid for bench.py / the sweep, not part of the
+    reference path."""
+    import time
+    require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    info = L.device_info(dev.index or 0)
+    sink = torch.zeros(512 * info["sm_count"], dtype=torch.float32, device=dev)
+    fma = C.c_double(0.0)
+
+    def run(iters: int) -> float:
+        with torch.cuda.device(dev):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(L.lib().kmsr_fp32_probe(_ptr(sink), int(iters), C.byref(fma), _stream(dev)))
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1)
+
+    ms = run(2000)                                      # sizes the launches; also the warm-up
+    per_iter = max(ms, 1e-3) / 2000
+    burst = 0.0
+    for _ in range(5):
+        time.sleep(0.05)
+        it = max(200, int(2.0 / per_iter))
+        m = run(it)
+        burst = max(burst, 2.0 * fma.value / (m * 1e-3) / 1e12)
+    it = max(2000, int(sustained_ms / per_iter))
+    m = run(it)
+    sustained = 2.0 * fma.value / (m * 1e-3) / 1e12
+    return {"burst": burst, "sustained": sustained}

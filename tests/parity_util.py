@@ -13,7 +13,9 @@ of such a result, so the criterion is applied in two parts:
       (the bar, discounting only the reference's own measured deviation from the exact value).
 
 `pure` = max|ours - reference| / range is also returned; callers assert pure <= 1e-5 wherever the
-reference's noise allows it (all textured patches, every golden case except the two water ones).
+reference's MEASURED deviation from the exact value is below half the bar (no exemption by case name: on this
+repository's fixtures that is every textured patch and every golden case except the two water ones, where
+the reference itself is 1.2e-5 / 1.4e-5 x range from exact -- tests/test_oracle_golden.py pins that evidence).
 `exact` is the fp64 evaluation of C_30:93-124 by oracle/oracle.c with the reference's own
 fp32-normalised kernel.
 """
@@ -34,9 +36,10 @@ def exact_degrade(img, kernel, factor, zero_pad=False, decimate=False):
     return oracle_c.degrade(img, kn, factor, zero_pad=zero_pad, decimate=decimate, f64=True)
 
 
-def check_pixels(out, ref, img, exact=None, noise=None, name=""):
+def check_pixels(out, ref, img, exact=None, noise=None, name="", detail=False):
     """out/ref [C,Ho,Wo], img [C,H,W].  `noise` (float64, already scaled) is added to `exact`.
-    Returns the pure metric; raises AssertionError when the criterion fails."""
+    Returns the pure metric (with `detail`: a dict that also holds the reference's own measured deviation from the
+    exact value and the fraction of pixels over the plain bar); raises AssertionError when the criterion fails."""
     rng = orc.band_range(img)
     o = out.astype(np.float64)
     finite = np.isfinite(ref)
@@ -53,4 +56,7 @@ def check_pixels(out, ref, img, exact=None, noise=None, name=""):
     r_ex = np.where(finite, np.abs(ref.astype(np.float64) - ex), 0.0) / rng
     assert (d_ex <= EXACT_TOL + slack).all(), (name, "vs exact", float(d_ex.max()))
     assert (d_ref <= PIX_TOL + r_ex + slack).all(), (name, "vs reference", pure, float(r_ex.max()))
+    if detail:
+        return {"pure": pure, "ref_vs_exact": float(r_ex.max()), "ours_vs_exact": float(d_ex.max()),
+                "frac_over_bar": float((d_ref > PIX_TOL).mean()), "ref_frac_over_bar": float((r_ex > PIX_TOL).mean())}
     return pure

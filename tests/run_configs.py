@@ -31,7 +31,8 @@ from oracle import oracle_c  # noqa: E402
 
 C, P = 5, 256
 HBM_PEAK = 6448.4
-FP32_PEAK_TFLOPS = 2 * 36.6          # scratch/ffma2_probe.cu: 36.6 TFMA/s sustained with FFMA2 on this pool's B200
+FP32_PEAK_TFLOPS = 2 * 36.6          # scratch/ffma2_probe.cu: 36.6 TFMA/s sustained with FFMA2 on this pool's B200;
+                                     # config5 replaces it by the in-process probe (ops.fp32_peak_tflops) when it runs
 try:
     HBM_PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
@@ -162,39 +163,66 @@ def config3(args, rank, world, dev):
            "algo": _lib.last_algo(), "ms_pairs": ms_pairs, "pairs_per_s": n_total / (ms_pairs * 1e-3),
            "ms_pairs_plus_stats": ms_all, "pairs_per_s_with_stats": n_total / (ms_all * 1e-3),
            "ms_pairs_plus_stats_unfused": ms_unfused, "pairs_per_s_with_stats_unfused": n_total / (ms_unfused * 1e-3),
-           "hbm_gbs_pairs": (4 * C * P * P + 2 * 4 * C * 1024) * n / (ms_pairs * 1e-3) / 1e9, "count": count}
+           "hbm_gbs_pairs": (4 * C * P * P + 2 * 4 * C * 1024) * n / (ms_pairs * 1e-3) / 1e9, "count": count,
+           "collective": f"all_reduce(SUM) of {2 * C + 1} float64 over {world} rank(s), inside the timed region"}
     out["hbm_frac_pairs"] = out["hbm_gbs_pairs"] / HBM_PEAK
+
+    # ---- statistics of the FULL set (every rank checks its own shard against fp64 on the device, worst over ranks) ----
+    m64 = torch.empty((n, C), dtype=torch.float64, device=dev)
+    s64 = torch.empty((n, C), dtype=torch.float64, device=dev)
+    for a0 in range(0, n, 512):
+        x = hr[a0:a0 + 512].double().flatten(2)
+        m64[a0:a0 + 512] = x.mean(dim=2)
+        s64[a0:a0 + 512] = x.std(dim=2, unbiased=False)
+    worst = torch.stack([((res["m"] - m64).abs() / m64.abs()).max(), ((res["s"] - s64).abs() / s64).max()])
+    # ---- the all-reduced sums against ONE process summing every rank's per-patch values (gathered) ----
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        gm = [torch.empty_like(res["m"]) for _ in range(world)]
+        gs = [torch.empty_like(res["s"]) for _ in range(world)]
+        dist.all_gather(gm, res["m"].contiguous())
+        dist.all_gather(gs, res["s"].contiguous())
+        gm, gs = torch.cat(gm), torch.cat(gs)
+    else:
+        gm, gs = res["m"], res["s"]
+    one_mean = (gm.sum(dim=0) / gm.shape[0]).cpu().numpy()
+    one_std = (gs.sum(dim=0) / gs.shape[0]).cpu().numpy()
+    gather_rel = float(max(np.abs(one_mean - avg_mean).max() / np.abs(one_mean).max(),
+                           np.abs(one_std - avg_std).max() / np.abs(one_std).max()))
+    assert count == n_total and gather_rel <= 1e-12, (count, n_total, gather_rel)
+    assert float(worst.max()) <= 1e-6, worst
+    out["stats_parity"] = {"set": f"all {n_total} patches (worst over {world} rank(s))", "mean_rel": float(worst[0]),
+                           "std_rel": float(worst[1]), "bar": 1e-6, "allreduce_vs_single_process_rel": gather_rel,
+                           "allreduce_bar": 1e-12, "avg_mean": [float(v) for v in avg_mean],
+                           "avg_std": [float(v) for v in avg_std]}
     if rank == 0:
-        # pixels: first 1024 + 1024 random patches against the C_30 -> E chain of the oracle
-        pick = np.concatenate([np.arange(min(1024, n)), np.random.RandomState(5).choice(n, min(1024, n), replace=False)])
-        pick = np.unique(pick)[: args.c3_check]
+        # pixels against the C_30 -> E chain of the oracle: half of the sample from the textured half of the shard,
+        # half from the water half (first patches of each + random ones), so every world size checks both regimes
+        half = max(1, args.c3_check // 2)
+        rs = np.random.RandomState(5)
+        tex = np.unique(np.concatenate([np.arange(min(half // 2, n // 2)), rs.choice(n // 2, min(half, n // 2), replace=False)]))[:half]
+        wat = n // 2 + np.unique(np.concatenate([np.arange(min(half // 2, n - n // 2)),
+                                                 rs.choice(n - n // 2, min(half, n - n // 2), replace=False)]))[:half]
+        pick = np.concatenate([tex, wat])
         hs = hr[torch.from_numpy(pick).to(dev)].cpu().numpy()
         ls = lr[torch.from_numpy(pick).to(dev)].cpu().numpy()
-        worst = {"textured": 0.0, "water": 0.0, "water_vs_exact": 0.0, "ref_water_vs_exact": 0.0}
+        worst_px = {"textured": 0.0, "water": 0.0, "water_vs_exact": 0.0, "ref_water_vs_exact": 0.0}
         kn = oracle_c.normalize_kernel(kb[0])
         for j, i in enumerate(pick):
             ref = orc.apply_kernel_degradation(torch.from_numpy(hs[j]), torch.from_numpy(kb[0]), 8).numpy() + pool_np[nidx[i]]
             r = orc.band_range(hs[j])
             e = float((np.abs(ls[j].astype(np.float64) - ref) / r).max())
             if i < n // 2:
-                worst["textured"] = max(worst["textured"], e)
+                worst_px["textured"] = max(worst_px["textured"], e)
             else:
-                worst["water"] = max(worst["water"], e)
-                if j % 16 == 0:
+                worst_px["water"] = max(worst_px["water"], e)
+                if j % 8 == 0:
                     ex = oracle_c.degrade(hs[j], kn, 8, f64=True) + pool_np[nidx[i]].astype(np.float64)
-                    worst["water_vs_exact"] = max(worst["water_vs_exact"], float((np.abs(ls[j] - ex) / r).max()))
-                    worst["ref_water_vs_exact"] = max(worst["ref_water_vs_exact"], float((np.abs(ref - ex) / r).max()))
-        out["pixel_parity"] = {"checked": int(len(pick)), **worst, "bar": 1e-5}
-        # statistics of this rank's shard against fp64 on the device
-        m64 = torch.empty((n, C), dtype=torch.float64, device=dev)
-        s64 = torch.empty((n, C), dtype=torch.float64, device=dev)
-        for a0 in range(0, n, 512):
-            x = hr[a0:a0 + 512].double().flatten(2)
-            m64[a0:a0 + 512] = x.mean(dim=2)
-            s64[a0:a0 + 512] = x.std(dim=2, unbiased=False)
-        out["stats_parity"] = {"mean_rel": float(((res["m"] - m64).abs() / m64.abs()).max()),
-                               "std_rel": float(((res["s"] - s64).abs() / s64).max()), "bar": 1e-6,
-                               "avg_mean": [float(v) for v in avg_mean], "avg_std": [float(v) for v in avg_std]}
+                    worst_px["water_vs_exact"] = max(worst_px["water_vs_exact"], float((np.abs(ls[j] - ex) / r).max()))
+                    worst_px["ref_water_vs_exact"] = max(worst_px["ref_water_vs_exact"], float((np.abs(ref - ex) / r).max()))
+        out["pixel_parity"] = {"checked": int(len(pick)), "checked_textured": int(len(tex)), "checked_water": int(len(wat)),
+                               **worst_px, "bar": 1e-5}
     return out
 
 
@@ -228,8 +256,9 @@ def config4(args, rank, world, dev):
     kb, _ = bank()
     H = W = args.c4_size
     hp, wp, stride = CUT.patch_grid(H, W)
-    i0, i1 = rng.shard_range(hp, rank, world)                     # patch-grid rows of this rank
-    full = device_scene(77, H, W, dev)
+    per_rank = getattr(args, "c4_scene_per_rank", False)          # bench.py: one whole scene per GPU (weak scaling)
+    i0, i1 = (0, hp) if per_rank else rng.shard_range(hp, rank, world)   # patch-grid rows of this rank
+    full = device_scene(77 + (rank if per_rank else 0), H, W, dev)
     slab = full[:, i0 * stride:(i1 - 1) * stride + P, :].contiguous() if i1 > i0 else full[:, :0]
     del full
     raw = slab.clone()
@@ -282,11 +311,12 @@ def config4(args, rank, world, dev):
         dist.all_reduce(kept)
     kept = int(kept.item())
     scene_bytes = 4 * C * H * W
-    out = {"config": 4, "workload": f"A_00 tiling of a [5,{H},{W}] scene (stride 128) + degrade + noise on kept windows, {world} GPU(s)",
-           "algo": algo_after, "candidates": hp * wp, "kept": kept, "ms_scene_total": ms, "ms_degrade_only": ms_deg,
+    scenes = world if per_rank else 1
+    out = {"config": 4, "workload": f"A_00 tiling of {scenes} [5,{H},{W}] scene(s) (stride 128) + degrade + noise on kept windows, {world} GPU(s)",
+           "algo": algo_after, "scenes": scenes, "candidates": hp * wp * scenes, "kept": kept, "scenes_per_s_fused": scenes / (ms_fused * 1e-3), "ms_scene_total": ms, "ms_degrade_only": ms_deg,
            "ms_scene_total_fused": ms_fused, "kept_pairs_per_s_total_fused": kept / (ms_fused * 1e-3),
            "kept_pairs_per_s_total": kept / (ms * 1e-3), "kept_pairs_per_s_degrade": kept / (ms_deg * 1e-3),
-           "unique_bytes_gbs_degrade": (scene_bytes + kept * 2 * 4 * C * 1024) / (ms_deg * 1e-3) / 1e9,
+           "unique_bytes_gbs_degrade": (scene_bytes * scenes + kept * 2 * 4 * C * 1024) / (ms_deg * 1e-3) / 1e9,
            "patchwise_bytes_gbs_degrade": kept * (4 * C * P * P + 2 * 4 * C * 1024) / (ms_deg * 1e-3) / 1e9}
     if rank == 0 and state["k"] > 0:
         ij = state["ij"].cpu().numpy()
@@ -321,13 +351,27 @@ def config4(args, rank, world, dev):
 
 def config5(args, rank, world, dev):
     """Roofline sweep: kernel size x patch size x factor at 1 GPU, HR batch >= --c5-gb GB."""
+    global FP32_PEAK_TFLOPS
+    fp32_src = "scratch/ffma2_probe.cu (FFMA2, measured earlier)"
+    try:
+        probe = ops.fp32_peak_tflops(dev)
+        FP32_PEAK_TFLOPS = float(probe["burst"])            # sweep cells are millisecond launches timed alone
+        fp32_src = (f"kmsr_fp32_probe, packed FFMA2 chains, measured in this run: burst {probe['burst']:.1f} TFLOP/s (used), "
+                    f"sustained under the power cap {probe['sustained']:.1f} TFLOP/s")
+    except Exception:
+        pass
     rows = []
+    cells = getattr(args, "c5_cells", None)                       # bench.py: a few named cells instead of all 60
     for k in (11, 13, 15, 21, 31):
         kern = torch.from_numpy(synth.softmax_kernels(k, 7)).to(dev)
         for p in (64, 128, 256, 512):
+            if cells is not None and not any(c[0] == k and c[1] == p for c in cells):
+                continue
             n = max(8, int(args.c5_gb * 1e9 / (4 * C * p * p)))
             hr = synth_hr_device(n, 900 + p, dev, size=p)
             for s in (2, 4, 8):
+                if cells is not None and (k, p, s) not in cells:
+                    continue
                 pb = ops.prepare_kernels(kern, s)
                 ho = p // s
                 out = torch.empty((n, C, ho, ho), device=dev)
@@ -347,9 +391,9 @@ def config5(args, rank, world, dev):
                              "fp32_frac": 2 * fma / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
                              "flop_per_byte": 2 * fma / by})
             del hr
-    # spot parity on the extremes (tiled kernel, odd shapes): 2 patches each against the oracle
+    # spot parity on the extremes: 2 patches each against the oracle
     par = []
-    for k, p, s in ((11, 64, 2), (31, 128, 4), (21, 512, 8), (15, 256, 2)):
+    for k, p, s in (((11, 64, 2), (31, 128, 4), (21, 512, 8), (15, 256, 2)) if cells is None else cells[:4]):
         kern = synth.softmax_kernels(k, 7)
         h = synth.make_hr(2, 31 + k, "textured", size=p)
         lr = ops.degrade_batch(torch.from_numpy(h).to(dev), torch.from_numpy(kern).to(dev), factor=s).cpu().numpy()
@@ -359,7 +403,7 @@ def config5(args, rank, world, dev):
             e = max(e, float((np.abs(lr[i].astype(np.float64) - ref) / orc.band_range(h[i])).max()))
         par.append({"k": k, "P": p, "s": s, "ours_vs_ref": e})
     return {"config": 5, "workload": "roofline sweep k x P x s, 1 GPU", "hbm_peak_gbs": HBM_PEAK,
-            "fp32_peak_tflops": FP32_PEAK_TFLOPS, "fp32_peak_source": "scratch/ffma2_probe.cu (FFMA2, measured)",
+            "fp32_peak_tflops": FP32_PEAK_TFLOPS, "fp32_peak_source": fp32_src,
             "rows": rows, "parity": par, "bar": 1e-5}
 
 

@@ -63,11 +63,17 @@ def test_golden_degrade_cases(K, golden, synth, algo):
         out = K.ops.degrade_batch(torch.from_numpy(img).cuda().unsqueeze(0), k.cuda(), factor=f,
                                   algo=algo)[0].cpu().numpy()
         assert out.shape == ref.shape, name
-        worst[name] = check_pixels(out, ref, img, exact_degrade(img, kern, f), name=name)
-    # the pure bar holds wherever the reference's own fp32 noise allows it (parity_util docstring)
-    bad = {k: v for k, v in worst.items() if not v <= PIX_TOL and "water" not in k}
+        worst[name] = check_pixels(out, ref, img, exact_degrade(img, kern, f), name=name, detail=True)
+    # The plain north-star bar (max |ours - ref| <= 1e-5 x range) is asserted wherever the reference's own MEASURED
+    # deviation from the exact value of its formula leaves room for it (< half the bar): no exemption by name.  Where the
+    # reference itself sits further than that from exact, |ours - ref| may exceed the bar by at most that deviation
+    # (check_pixels asserted it per pixel) and ours must still be within 5e-6 of exact.
+    bad = {k: v for k, v in worst.items() if v["pure"] > PIX_TOL and v["ref_vs_exact"] < 0.5 * PIX_TOL}
     assert not bad, (bad, worst)
-    assert max(worst.values()) <= 2e-5, worst
+    noisy = {k: v for k, v in worst.items() if v["ref_vs_exact"] >= 0.5 * PIX_TOL}
+    assert all(v["pure"] <= PIX_TOL + v["ref_vs_exact"] and v["ours_vs_exact"] <= 5e-6 for v in noisy.values()), noisy
+    # the audit trail: which cases needed the discount, and how many of their pixels are over the plain bar
+    print({k: (round(v["pure"] * 1e5, 3), round(v["ref_vs_exact"] * 1e5, 3), v["frac_over_bar"]) for k, v in noisy.items()})
 
 
 def test_dropin_signatures_match_reference_outputs(K, golden, synth):
@@ -693,15 +699,21 @@ def test_shapes_the_streaming_kernels_hand_to_each_other(K, synth, bank):
     K.ops.degrade_batch(hr[:, :, :250, :250].contiguous(), kd, factor=8)          # 250 is not a multiple of 8
     assert K.lib.last_algo() == "tiled"
     K.ops.degrade_batch(hr[:, :, :128, :128].contiguous(), kd, factor=4)
+    assert K.lib.last_algo() == "box"
+    K.ops.degrade_batch(hr[:, :, :128, :128].contiguous(), kd, factor=8)
     assert K.lib.last_algo() == "stream"
-    # FP32-bound shapes go to the register-tile kernel: factor 2, factor 4 on 64-wide patches, and the factor-4
-    # shapes the streaming kernel refuses (widths that are not 64 / 128 / 256 m)
+    # factor 2 / 4 and 64-wide patches go to the TMA box-tile kernel; what it refuses (H % 8, W % 16) falls to the
+    # register-tile kernel (any H / W / strides)
     r2 = K.ops.degrade_batch(hr, kd, factor=2)
-    assert K.lib.last_algo() == "reg"
+    assert K.lib.last_algo() == "box"
     s2 = K.ops.degrade_batch(hr, kd, factor=2, algo="stream")
     assert K.lib.last_algo() == "stream" and float(((r2 - s2).abs() / rngs).max()) <= 2e-6
+    g2 = K.ops.degrade_batch(hr, kd, factor=2, algo="reg")
+    assert K.lib.last_algo() == "reg" and float(((r2 - g2).abs() / rngs).max()) <= 2e-6
     K.ops.degrade_batch(hr[:, :, :64, :64].contiguous(), kd, factor=4)
-    assert K.lib.last_algo() == "reg"
+    assert K.lib.last_algo() == "box"
+    K.ops.degrade_batch(hr[:, :, :64, :64].contiguous(), kd, factor=8)
+    assert K.lib.last_algo() == "box"
     K.ops.degrade_batch(hr[:, :, :100, :36].contiguous(), kd, factor=4)
     assert K.lib.last_algo() == "reg"
     # strided views: a channel slice of a wider tensor still streams (16-byte aligned strides)
@@ -856,3 +868,113 @@ def test_non_square_and_short_patches(K, synth, bank, h, w, k, s, algo):
     for i in range(n):
         ref = orc.apply_kernel_degradation(torch.from_numpy(hr[i]), torch.from_numpy(kern), s).numpy()
         check_pixels(lr[i], ref, hr[i], exact_degrade(hr[i], kern, s), name=f"{h}x{w} k{k} s{s} #{i}")
+
+
+def test_indices_are_range_checked_at_the_boundary(K, synth, bank):
+    """kidx >= nK / nidx >= nPool / crop offsets outside the image are out-of-bounds device reads inside the kernels:
+    host arrays are rejected by the wrapper (IndexError, as noise_pool[idx] raises in the reference, E:72-74), device
+    arrays through kmsr_validate_indices when the caller opts in, and the C entry returns KMSR_E_INVALID."""
+    import ctypes as C
+    kb, sb = bank
+    hr = torch.from_numpy(synth.make_hr(4, 77, "textured")).cuda()
+    pool = torch.from_numpy(synth.make_noise_pool(8, 1)).cuda()
+    kd = torch.from_numpy(kb).cuda()
+    good_k, good_n = np.array([0, 9, 3, 1], np.int32), np.array([7, 0, 2, 5], np.int32)
+    K.ops.degrade_batch(hr, kd, kidx=good_k, sigma=torch.from_numpy(sb), pool=pool, nidx=good_n, noise_mode="sigma")
+    for bad_k, bad_n in ((np.array([0, 10, 3, 1], np.int32), good_n), (good_k, np.array([7, 0, 8, 5], np.int32)),
+                         (np.array([0, -1, 3, 1], np.int32), good_n)):
+        with pytest.raises(IndexError):
+            K.ops.degrade_batch(hr, kd, kidx=bad_k, sigma=torch.from_numpy(sb), pool=pool, nidx=bad_n, noise_mode="sigma")
+    with pytest.raises(ValueError):                                   # one index per patch
+        K.ops.degrade_batch(hr, kd, kidx=good_k[:3], sigma=torch.from_numpy(sb), pool=pool, nidx=good_n, noise_mode="sigma")
+    # device-resident indices: trusted by default, checked on request
+    bad_dev = torch.tensor([7, 0, 8, 5], dtype=torch.int32, device="cuda")
+    with pytest.raises(IndexError):
+        K.ops.degrade_batch(hr, kd, kidx=torch.from_numpy(good_k).cuda(), sigma=torch.from_numpy(sb), pool=pool, nidx=bad_dev,
+                            noise_mode="sigma", validate=True)
+    K.ops.degrade_batch(hr, kd, kidx=torch.from_numpy(good_k).cuda(), sigma=torch.from_numpy(sb), pool=pool,
+                        nidx=torch.from_numpy(good_n).cuda(), noise_mode="sigma", validate=True)
+    # the C entry itself
+    scratch = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = K.lib.lib().kmsr_validate_indices(C.c_void_p(bad_dev.data_ptr()), 4, 8, C.c_void_p(scratch.data_ptr()), b"nidx", None)
+    assert rc == K.lib.E_INVALID and "1 of 4" in K.lib.last_error()
+    rc = K.lib.lib().kmsr_validate_indices(C.c_void_p(bad_dev.data_ptr()), 4, 9, C.c_void_p(scratch.data_ptr()), b"nidx", None)
+    assert rc == 0
+    # add_noise / crop_sub wrappers
+    with pytest.raises(IndexError):
+        K.ops.add_noise_batch(torch.zeros((4, 5, 32, 32), device="cuda"), pool, np.array([0, 1, 2, 8], np.int32))
+    geo = torch.randn((5, 64, 80), device="cuda")
+    den = torch.randn((5, 64, 80), device="cuda")
+    K.ops.crop_sub(geo, den, [0, 32], [48, 0], 32)
+    with pytest.raises(IndexError):
+        K.ops.crop_sub(geo, den, [0, 33], [48, 0], 32)               # top + crop > H
+    with pytest.raises(ValueError):
+        K.ops.crop_sub(geo, den[:, :, :64], [0], [0], 32)            # geo - den would not broadcast (D:88)
+    with pytest.raises(ValueError):
+        K.ops.crop_sub(geo, den, [0], [0], 65)                       # D:44-45
+
+
+def test_fused_statistics_on_shapes_the_headline_kernel_refuses(K, synth, bank):
+    """degrade_batch_stats on a 512-wide band (the fused path needs W == 256): the two kernels run back to back and the
+    statistics are real, not an unwritten workspace (an uninitialised probe once let this shape claim the fused path);
+    asking for a kernel that cannot fuse is reported, not silently ignored."""
+    kb, _ = bank
+    hr = torch.randn((3, 5, 64, 512), device="cuda") * 2.0 + 40.0
+    lr, m, s = K.ops.degrade_batch_stats(hr, torch.from_numpy(kb[1]).cuda(), factor=8)
+    x = hr.double().flatten(2)
+    assert float(((m - x.mean(dim=2)).abs() / x.mean(dim=2).abs()).max()) <= 1e-6
+    assert float(((s - x.std(dim=2, unbiased=False)).abs() / x.std(dim=2, unbiased=False)).max()) <= 1e-6
+    ref = K.ops.degrade_batch(hr, torch.from_numpy(kb[1]).cuda(), factor=8)
+    assert torch.equal(lr, ref)
+    # the headline shape through an explicitly requested non-fusing kernel: statistics still right
+    hr2 = torch.randn((2, 5, 256, 256), device="cuda") + 10.0
+    lr2, m2, s2 = K.ops.degrade_batch_stats(hr2, torch.from_numpy(kb[1]).cuda(), factor=8, algo="stream")
+    assert K.lib.last_algo() == "stream"
+    x2 = hr2.double().flatten(2)
+    assert float(((m2 - x2.mean(dim=2)).abs() / x2.mean(dim=2).abs()).max()) <= 1e-6
+    assert float(((s2 - x2.std(dim=2, unbiased=False)).abs() / x2.std(dim=2, unbiased=False)).max()) <= 1e-6
+
+
+@pytest.mark.parametrize("k,s,down", [(15, 8, "boxmean"), (7, 8, "boxmean"), (13, 2, "boxmean"), (13, 3, "decimate")])
+def test_tiled_kernel_pad_taps_never_meet_a_neighbouring_pixel(K, synth, k, s, down):
+    """The tiled fallback pads a composite row to a multiple of 4 taps; a pad tap (weight 0) times a NaN / Inf pixel up to
+    three columns right of an output's window would poison outputs the reference keeps finite.  Shapes with KWp > KW."""
+    kern = synth.softmax_kernels(k, 3)
+    h = w = 64
+    hr = synth.make_hr(1, 5150 + k, "textured", size=64)[0]
+    ho = len(range(0, h, s)) if down == "decimate" else h // s
+    for (c, y, x, val) in ((0, 20, 37, np.nan), (2, 0, 5, np.inf), (4, 63, 63, np.nan), (1, 33, 0, -np.inf)):
+        img = hr.copy()
+        img[c, y, x] = val
+        out = K.ops.degrade_batch(torch.from_numpy(img).cuda().unsqueeze(0), torch.from_numpy(kern).cuda(), factor=s,
+                                  down_mode=down, algo="tiled")[0].cpu().numpy()
+        # footprint by the definition: output (Y, X) of band c is non-finite iff its clamped window holds the pixel
+        p = k // 2
+        ys = np.arange(ho)[:, None, None] * s + np.arange(k + (s - 1 if down == "boxmean" else 0))[None, :, None] - p
+        xs = np.arange(ho)[:, None, None] * s + np.arange(k + (s - 1 if down == "boxmean" else 0))[None, :, None] - p
+        hit_y = (np.clip(ys, 0, h - 1) == y).any(axis=1)[:, 0]
+        hit_x = (np.clip(xs, 0, w - 1) == x).any(axis=1)[:, 0]
+        want = np.zeros((5, ho, ho), dtype=bool)
+        want[c] = hit_y[:, None] & hit_x[None, :]
+        assert np.array_equal(~np.isfinite(out), want), (k, s, down, c, y, x)
+
+
+def test_two_rank_nccl_all_reduce_of_the_statistics(K, tmp_path):
+    """Config 3 (pairs + fused statistics + the design's only collective) on two GPUs under torchrun: the all-reduced
+    sums must equal one process summing the gathered per-patch values (asserted inside run_configs.config3).  Skipped on
+    a single-GPU box; bench.py runs the same block at every N of the driver's scaling run."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "c3.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(root, "tests", "run_configs.py"), "--configs", "3", "--c3-patches", "512",
+           "--c3-check", "64", "--reps", "1", "--out", str(out)]
+    subprocess.run(cmd, check=True, timeout=600, cwd=root)
+    r = json.load(open(out))[0]
+    assert r["count"] == 1024 and r["stats_parity"]["allreduce_vs_single_process_rel"] <= 1e-12
+    assert r["pixel_parity"]["checked_water"] > 0 and r["pixel_parity"]["textured"] <= 1e-5

@@ -158,8 +158,12 @@ def test_product_never_imports_the_oracle():
     for line in bench.splitlines():
         if "import" in line and "oracle" in line:
             assert line.startswith("    "), f"bench.py imports the oracle at module level: {line}"
-    for fn in ("def cpu_reference_pairs_per_s", "def run_reference"):
+    for fn in ("def _quiet_reference_loader", "def time_reference", "def run_reference", "def parity_audit"):
         assert fn in bench
+    # the oracle appears only in the reference arm, the cpu_baseline leg (timed BEFORE any GPU work) and the parity audit /
+    # configs block that run AFTER the timed regions: nothing between the first and the last timed event touches it
+    timed = bench[bench.index("# ---- device-resident throughput"):bench.index("# ---- parity audit on the CPU sample")]
+    assert "oracle" not in timed and "refarm" not in timed
 
 
 _WORKER = r"""
