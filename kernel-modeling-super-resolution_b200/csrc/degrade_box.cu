@@ -67,6 +67,8 @@ struct BCfg {
 };
 
 struct BoxArgs {
+    const float* hr;        // band mode: rows 0 and H-1 are also fetched with plain bulk copies
+    long long sN, sC, sH;
     const float* comp;      // [nK, C, KW, KWp]
     int KWp;
     const float* dsum;
@@ -82,9 +84,25 @@ struct BoxArgs {
     int NQ;                 // staged row groups of 8
     int WB;                 // staged row pitch in floats = box width (odd multiple of 4)
     int planeF;             // floats per row-residue plane: NQ WB rounded up to 128 bytes (a TMA destination)
-    int regionF;            // floats per staged region (8 planes)
+    int regionF;            // floats per staged region (8 planes; band mode: + the two clamp rows, see clamp_floats)
+    int clamp_rows;         // band mode: the two clamp rows are staged
     int replicate, noise_mode;
 };
+
+// Band mode, replicate padding: rows above / below the band clamp to row 0 / H-1.  A lane that clamps would read another
+// row-residue plane at the row group q its neighbour reads -- planes are 128-byte aligned, so that is a bank conflict on
+// every load of 12 of a thread's 20 rows (measured: 35 % excess wavefronts on the 64-wide factor-8 cells, ncu r2d).
+// Two extra staged rows behind the eight planes hold a copy of row H-1 at the bank offset of row group 0 and a copy of
+// row 0 at the bank offset of row group 7: exactly the two bank groups the unclamped lanes of a quarter-warp leave free.
+// clampF floats = [row H-1 | gap | row 0], the gap chosen so that row 0 starts at 7 WB floats modulo 32.
+__host__ __device__ inline int clamp_top_offset(int WB) { return WB + ((7 * WB - WB) % 32 + 32) % 32; }
+__host__ __device__ inline int clamp_floats(int WB) { return (clamp_top_offset(WB) + WB + 31) / 32 * 32; }
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
                                             uint32_t bar) {
@@ -137,11 +155,18 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
     const int ry0 = BAND ? 0 : tileY0 - G::PADU;                  // HR row of staged row 0 (a multiple of 8)
 
     // ---- TMA: one box per row residue j (rows j, j+8, ... of the staged window), 8 lanes issue in parallel ----
+    const bool clamp_rows = BAND && a.clamp_rows;
     if (BAND || warp == 0) {
-        if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)(a.NQ * a.WB));
+        if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)(a.NQ * a.WB) + (clamp_rows ? 8u * (uint32_t)a.W : 0u));
         __syncwarp();
         if (lane < 8)
             tma_load_5d(smem_u32(region + (size_t)lane * a.planeF), &tmap, rx0, lane, ry0 / 8, c, (int)n, bar);
+        else if (clamp_rows && lane < 10) {
+            const float* band0 = a.hr + n * a.sN + (long long)c * a.sC;
+            const int top = lane == 8;                   // row 0 -> row group 7, row H-1 -> row group 0 of the clamp plane
+            bulk_load(smem_u32(region + (size_t)8 * a.planeF + (top ? clamp_top_offset(a.WB) : 0) + G::PADL),
+                      band0 + (top ? 0 : (long long)(a.H - 1) * a.sH), 4u * (uint32_t)a.W, bar);
+        }
     }
 
     // ---- per-band parameters and the composite kernel (shifted by one float when the first tap is odd): cp.async, so
@@ -177,8 +202,6 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
     const bool replicate = a.replicate != 0;
     const bool ledge = replicate && tileX0 + 16 * lx == 0;        // halo columns left of the band in this thread's segment
     const bool redge = replicate && colsLeft == 16;               // ... right of the band (W % 16 == 0: box_shape_ok)
-    // warp-uniform guards: only warps that hold an edge thread issue the substitution moves at all
-    const bool wledge = __any_sync(0xffffffffu, ledge), wredge = __any_sync(0xffffffffu, redge);
     const float* tbase = region + 16 * lx;
 
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -211,7 +234,12 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
         const int cl_row = min(max(hr_row, 0), a.H - 1);
         const int t = ((replicate || BAND) ? cl_row : hr_row) - ry0;
         KMSR_DASSERT(t >= 0 && t < 8 * a.NQ && 16 * lx + 4 * G::NL4 <= a.WB);     // the segment lies inside the staged region
-        const ulonglong2* prow = reinterpret_cast<const ulonglong2*>(tbase + (size_t)(t & 7) * a.planeF + (t >> 3) * a.WB);
+        const float* pf = tbase + (size_t)(t & 7) * a.planeF + (t >> 3) * a.WB;
+        if (clamp_rows) {                                 // band mode: clamped rows come from the conflict-free copies
+            if (hr_row < 0) pf = tbase + (size_t)8 * a.planeF + clamp_top_offset(a.WB);
+            if (hr_row >= a.H) pf = tbase + (size_t)8 * a.planeF;
+        }
+        const ulonglong2* prow = reinterpret_cast<const ulonglong2*>(pf);
 #pragma unroll
         for (int i = 0; i < G::NL4; ++i) {
             const ulonglong2 v = prow[i];
@@ -221,17 +249,18 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
 #pragma unroll
             for (int i = 0; i < G::NPL; ++i) P[i] = 0ull;
         }
-        if (wledge) {
+        // (a warp-uniform branch around these predicated moves measured 5-10 % slower on the large kernels, r2h)
+        if (ledge) {
             const float v = lo2(P[G::PADL / 2]);
             const u64 vv = pack2(v, v);
 #pragma unroll
-            for (int i = 0; i < G::PADL / 2; ++i) P[i] = ledge ? vv : P[i];
+            for (int i = 0; i < G::PADL / 2; ++i) P[i] = vv;
         }
-        if (wredge) {
+        if (redge) {
             const float v = hi2(P[G::RPAIR - 1]);
             const u64 vv = pack2(v, v);
 #pragma unroll
-            for (int i = G::RPAIR; i < G::NPL; ++i) P[i] = redge ? vv : P[i];
+            for (int i = G::RPAIR; i < G::NPL; ++i) P[i] = vv;
         }
 #pragma unroll
         for (int i = 0; i < G::NPL; ++i) P[i] = add2(P[i], npv2);
@@ -378,24 +407,40 @@ int launch_box(const DegradeArgs& a, cudaStream_t st) {
     if ((wb / 4) % 2 == 0) wb += 4;
     t.WB = wb;
     t.planeF = (t.NQ * t.WB + 31) / 32 * 32;
-    t.regionF = 8 * t.planeF;
+    t.hr = a.hr; t.sN = a.N > 1 ? a.sN : 0; t.sC = a.sC; t.sH = a.sH;
     t.replicate = a.pad_mode == KMSR_PAD_REPLICATE ? 1 : 0;
     t.noise_mode = a.noise_mode;
-    const size_t gbytes = (size_t)(t.regionF + G::KW * G::WP) * 4;
-    // band mode: the bands per CTA (1-4 warps) that keep the most warps resident (ties: larger CTAs)
+    // band mode: the bands per CTA (1-4 warps) that keep the most warps resident (ties: larger CTAs).  The two clamp rows
+    // (conflict-free replicate rows, see clamp_floats) are worth 10-27 % on the factor-4 / factor-8 bands; at factor 2
+    // (FP32-bound) they are staged only when they do not cost a resident warp.
     t.groups = 1;
+    t.clamp_rows = 0;
+    size_t gbytes = (size_t)(8 * t.planeF + G::KW * G::WP) * 4;
     if (band_mode) {
-        long long best = -1;
-        for (int g = 4; g >= 1; --g) {
-            const size_t bytes = 128 + g * gbytes;
-            if (bytes > (size_t)max_smem) continue;
-            long long ctas = sm_smem / (bytes + 1024);
-            if (ctas > 32) ctas = 32;
-            if (ctas * g > 16) ctas = 16 / g;                        // 16 warps per SM is plenty at <= 255 registers
-            if (ctas * g > best) { best = ctas * g; t.groups = g; }
-        }
-        KMSR_REQUIRE(best > 0, KMSR_E_UNSUPPORTED, "degrade (box): k=%d factor=%d does not fit shared memory", K, S);
+        cudaFuncAttributes fa;
+        KMSR_CUDA_OK(cudaFuncGetAttributes(&fa, degrade_box_kernel<K, S, true>));
+        const long long reg_warps = 65536 / (32ll * ((fa.numRegs + 7) / 8 * 8));     // warps the register file holds
+        auto plan = [&](size_t per_band, int* groups) {
+            long long best = -1;
+            for (int g = 4; g >= 1; --g) {
+                const size_t bytes = 128 + g * per_band;
+                if (bytes > (size_t)max_smem) continue;
+                long long ctas = sm_smem / (bytes + 1024);
+                if (ctas > 32) ctas = 32;
+                if (ctas * g > reg_warps) ctas = reg_warps / g;
+                if (ctas * g > best) { best = ctas * g; *groups = g; }
+            }
+            return best;
+        };
+        int g0 = 1, g1 = 1;
+        const long long plain = plan(gbytes, &g0);
+        const size_t with_clamp = gbytes + (size_t)clamp_floats(t.WB) * 4;
+        const long long clamped = t.replicate ? plan(with_clamp, &g1) : -1;
+        KMSR_REQUIRE(plain > 0, KMSR_E_UNSUPPORTED, "degrade (box): k=%d factor=%d does not fit shared memory", K, S);
+        if (clamped > 0 && (S > 2 || clamped >= plain)) { t.clamp_rows = 1; t.groups = g1; gbytes = with_clamp; }
+        else t.groups = g0;
     }
+    t.regionF = (int)(gbytes / 4) - G::KW * G::WP;
     const size_t smem = 128 + (size_t)t.groups * gbytes;
     KMSR_REQUIRE(smem <= (size_t)max_smem, KMSR_E_UNSUPPORTED, "degrade (box): k=%d factor=%d needs %zu B of shared memory", K, S, smem);
 

@@ -13,24 +13,29 @@ constexpr int kProbeThreads = 512;       // 4 warps per scheduler
 constexpr int kProbeChains = 12;         // independent accumulator pairs per thread
 constexpr int kProbeRounds = 4;
 
+// The operand pattern is the degrade kernels': one weight pair held against a run of (pixel pair, accumulator pair)
+// operands, so the weight comes from the operand-reuse cache and an FFMA2 reads two 64-bit register operands.  With
+// three distinct register-pair operands per instruction the register file sustains one FFMA2 per THREE clocks, not
+// two (measured: 49.4 instead of 73 TFLOP/s, SM clock 1965 MHz, 515 W -- not the power cap): a probe written that way
+// under-reports the roofline.
 __global__ void __launch_bounds__(kProbeThreads, 1) ffma2_probe_kernel(float* sink, int iters, float w0) {
-    float a[2 * kProbeChains], w[8], d[8];
+    u64 A[kProbeChains], D[kProbeChains], W[kProbeRounds];
 #pragma unroll
-    for (int i = 0; i < 2 * kProbeChains; ++i) a[i] = threadIdx.x * 0.001f + i;
+    for (int i = 0; i < kProbeChains; ++i) {
+        A[i] = pack2(threadIdx.x * 0.001f + i, threadIdx.x * 0.002f - i);
+        D[i] = pack2(1.0f + threadIdx.x * 1e-3f + i, 0.5f - threadIdx.x * 1e-3f - i);
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { w[i] = w0 + i * 0.01f; d[i] = 1.0f + threadIdx.x * 1e-3f + i; }
-    u64* A = reinterpret_cast<u64*>(a);
-    const u64* W = reinterpret_cast<const u64*>(w);
-    const u64* D = reinterpret_cast<const u64*>(d);
+    for (int r = 0; r < kProbeRounds; ++r) W[r] = pack2(w0 + r * 0.01f, w0 - r * 0.01f);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int r = 0; r < kProbeRounds; ++r)
 #pragma unroll
-            for (int i = 0; i < kProbeChains; ++i) A[i] = fma2(W[(i + r) & 3], D[(i + 2 * r) & 3], A[i]);
+            for (int i = 0; i < kProbeChains; ++i) A[i] = fma2(W[r], D[(i + r) % kProbeChains], A[i]);
     }
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 2 * kProbeChains; ++i) s += a[i];
+    for (int i = 0; i < kProbeChains; ++i) s += lo2(A[i]) + hi2(A[i]);
     if (s == 123.456f) sink[blockIdx.x * blockDim.x + threadIdx.x] = s;      // keeps the chains alive, writes nothing
 }
 

@@ -355,9 +355,9 @@ def config5(args, rank, world, dev):
     fp32_src = "scratch/ffma2_probe.cu (FFMA2, measured earlier)"
     try:
         probe = ops.fp32_peak_tflops(dev)
-        FP32_PEAK_TFLOPS = float(probe["burst"])            # sweep cells are millisecond launches timed alone
-        fp32_src = (f"kmsr_fp32_probe, packed FFMA2 chains, measured in this run: burst {probe['burst']:.1f} TFLOP/s (used), "
-                    f"sustained under the power cap {probe['sustained']:.1f} TFLOP/s")
+        FP32_PEAK_TFLOPS = float(max(probe["burst"], probe["sustained"]))     # the larger one: never flatter a cell
+        fp32_src = (f"kmsr_fp32_probe, packed FFMA2 chains with the degrade kernels' operand pattern, measured in this run: "
+                    f"~2 ms launches {probe['burst']:.1f} TFLOP/s, one 150 ms launch {probe['sustained']:.1f} TFLOP/s (the larger is used)")
     except Exception:
         pass
     rows = []
