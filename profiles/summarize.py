@@ -2,6 +2,7 @@
 """Turn one gpurun profiling call (scratch/run_prof.sh) into the tracked summaries under profiles/.
 
     python profiles/summarize.py r13            # reads gpurun_out/r13_tma.ncu-rep, r13_launches.csv, r13_bench.json
+    python profiles/summarize.py r2z box_13_256_2 r2     # any other capture gpurun_out/<tag>_<which>.ncu-rep, round prefix r2
 
 Writes profiles/<round>_<tag>_kernel.json (ncu --set full, one launch of the dominant kernel),
 profiles/<round>_<tag>_launches.csv (every launch of the bench command with its device time),
@@ -49,8 +50,11 @@ def num(v):
 
 
 def main():
+    global ROUND
     tag = sys.argv[1] if len(sys.argv) > 1 else "r13"
-    which = sys.argv[2] if len(sys.argv) > 2 else "tma"          # "tma" (bench.py capture) or "stream" (tools/stream_case.py)
+    which = sys.argv[2] if len(sys.argv) > 2 else "tma"          # "tma" (bench.py capture) or any other capture name
+    if len(sys.argv) > 3:
+        ROUND = sys.argv[3]
     rep = os.path.join(OUT, f"{tag}_{which}.ncu-rep")
     rows = ncu_csv(rep, "raw")
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -74,6 +78,9 @@ def main():
     sfx = "" if which == "tma" else f"_{which}"
     if which != "tma":
         plain = os.path.join(OUT, f"{tag}_plain3.log")
+        for cand in (os.path.join(OUT, f"{tag}_plain_{which}.log"), os.path.join(OUT, f"{tag}_plain_{which.split('_', 1)[-1]}.log")):
+            if os.path.isfile(cand):
+                plain = cand
         if os.path.isfile(plain):
             rec["plain_run"] = open(plain).read().strip().splitlines()[-1]
     if which == "tma" and os.path.isfile(bench):
@@ -104,7 +111,7 @@ def main():
         rec["launch_shares"] = {k: {"launches": v[0], "ns": v[1], "share": v[1] / allns} for k, v in tot.items()}
         # the timed region of bench.py holds only libkmsr launches (torch kernels above are the untimed synthetic-data
         # setup; prepare_kernels runs once in the constructor): share of each kernel inside a step
-        step = {k: v for k, v in tot.items() if "kmsr::" in k and "prepare_kernels" not in k}
+        step = {k: v for k, v in tot.items() if "kmsr::" in k and "prepare_kernels" not in k and "ffma2_probe" not in k}
         sns = sum(v[1] for v in step.values())
         rec["step_shares"] = {k: {"launches": v[0], "ns_per_launch": v[1] / v[0], "share_of_step": v[1] / sns}
                               for k, v in step.items()}
