@@ -117,7 +117,7 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
 // image rows are staged, halo rows clamp or are zeroed in registers); otherwise the four warps share one 128 x 128
 // tile (2 x 2 warps of 64 x 64) staged with its halo rows.
 template <int K, int S, bool BAND>
-__global__ void __launch_bounds__(kBoxThreads, 2)
+__global__ void __launch_bounds__(kBoxThreads, (BAND && S != 2) ? 3 : 2)      // factor-2 bands spill at 168 registers (r2n)
 degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
     using G = BCfg<K, S>;
     extern __shared__ __align__(128) unsigned char bsm[];
@@ -388,10 +388,9 @@ int launch_box(const DegradeArgs& a, cudaStream_t st) {
     using G = BCfg<K, S>;
     EncodeTiledFn enc = get_tensor_map_encoder();
     KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "degrade (box): cuTensorMapEncodeTiled is not available from the driver");
-    int dev = 0, max_smem = 0, sm_smem = 0;
+    int dev = 0, max_smem = 0;
     KMSR_CUDA_OK(cudaGetDevice(&dev));
     KMSR_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    KMSR_CUDA_OK(cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     const bool band_mode = a.H <= 64 && a.W <= 64;
     const int TW = band_mode ? 64 : 128;
     BoxArgs t;
@@ -417,18 +416,20 @@ int launch_box(const DegradeArgs& a, cudaStream_t st) {
     t.clamp_rows = 0;
     size_t gbytes = (size_t)(8 * t.planeF + G::KW * G::WP) * 4;
     if (band_mode) {
-        cudaFuncAttributes fa;
-        KMSR_CUDA_OK(cudaFuncGetAttributes(&fa, degrade_box_kernel<K, S, true>));
-        const long long reg_warps = 65536 / (32ll * ((fa.numRegs + 7) / 8 * 8));     // warps the register file holds
+        // resident warps per SM for g bands per CTA, as the runtime computes it (registers are allocated per scheduler:
+        // at 202 registers a scheduler holds two warps, so 3-warp CTAs leave a quarter of the slots empty -- a plain
+        // "register file / registers per warp" estimate picked exactly that for k = 11, ncu r2m)
+        auto kern_b = degrade_box_kernel<K, S, true>;
+        KMSR_CUDA_OK(cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        KMSR_CUDA_OK(cudaFuncSetAttribute(kern_b, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         auto plan = [&](size_t per_band, int* groups) {
             long long best = -1;
             for (int g = 4; g >= 1; --g) {
                 const size_t bytes = 128 + g * per_band;
                 if (bytes > (size_t)max_smem) continue;
-                long long ctas = sm_smem / (bytes + 1024);
-                if (ctas > 32) ctas = 32;
-                if (ctas * g > reg_warps) ctas = reg_warps / g;
-                if (ctas * g > best) { best = ctas * g; *groups = g; }
+                int ctas = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kern_b, 32 * g, bytes) != cudaSuccess) continue;
+                if ((long long)ctas * g > best) { best = (long long)ctas * g; *groups = g; }
             }
             return best;
         };
