@@ -978,3 +978,21 @@ def test_two_rank_nccl_all_reduce_of_the_statistics(K, tmp_path):
     r = json.load(open(out))[0]
     assert r["count"] == 1024 and r["stats_parity"]["allreduce_vs_single_process_rel"] <= 1e-12
     assert r["pixel_parity"]["checked_water"] > 0 and r["pixel_parity"]["textured"] <= 1e-5
+
+
+def test_resident_noise_pool_follows_the_host_array(K, synth):
+    """E.add_noise keeps the last host pool resident on the device.  The cache must notice a DIFFERENT pool of the same
+    shape (a freed pool's address is commonly reused by the next np.load) and an in-place edit of the same array."""
+    blurred = np.zeros((5, 32, 32), dtype=np.float32)
+    pool_a = np.full((4, 5, 32, 32), 1.0, dtype=np.float32)
+    np.random.seed(0)
+    out = K.E.add_noise(blurred, pool_a)
+    assert float(out.min()) == float(out.max()) == 1.0
+    addr = pool_a.__array_interface__["data"][0]
+    del pool_a
+    pool_b = np.full((4, 5, 32, 32), 2.0, dtype=np.float32)          # usually lands where pool_a was
+    out = K.E.add_noise(blurred, pool_b)
+    assert float(out.min()) == float(out.max()) == 2.0, (addr, pool_b.__array_interface__["data"][0])
+    pool_b[:] = 3.0                                                   # in-place edit of the cached array
+    out = K.E.add_noise(blurred, pool_b)
+    assert float(out.min()) == float(out.max()) == 3.0

@@ -298,3 +298,59 @@ def test_selector_weight_blobs_reproduce_the_reference_forward(golden):
     ref = sel.logits_library(torch.from_numpy(x)).numpy()
     assert np.abs(lg - ref).max() <= 2e-6 * np.abs(ref).max()
     assert np.array_equal(lg.argmax(1), ref.argmax(1))
+
+
+def test_reference_arm_loader_prefers_the_verbatim_reference(monkeypatch, tmp_path):
+    """oracle/refarm.py: the verbatim reference function when a copy is reachable (KMSR_REFERENCE_ROOT, baseline/_ref,
+    /root/reference), else the call-site port -- and both give the same pairs on the same inputs."""
+    import importlib
+    import torch
+    from oracle import kmsr_oracle as orc
+    from oracle import refarm
+    import kmsr_b200.synth as synth
+    hr = synth.make_hr(2, 5, "textured", size=64)
+    kb = np.stack([synth.softmax_kernels(13, 3), synth.softmax_kernels(13, 4)])
+    sb = np.linspace(0.7, 1.0, 10, dtype=np.float32).reshape(2, 5)
+    pool = synth.make_noise_pool(4, 1, size=8)
+    kidx, nidx = np.array([1, 0], np.int32), np.array([3, 2], np.int32)
+    want = orc.multi_kernel_pairs(hr, kb, sb, pool, kidx, nidx, 8)
+    # port: no reference reachable
+    monkeypatch.setenv("KMSR_REFERENCE_ROOT", str(tmp_path / "nowhere"))
+    monkeypatch.setattr(refarm, "_candidates", lambda: [str(tmp_path / "nowhere")])
+    refarm._cache.clear()
+    fn, kind, _ = refarm.load_apply()
+    assert kind == "port"
+    assert np.array_equal(refarm.multi_kernel_pairs(hr, kb, sb, pool, kidx, nidx, 8), want)
+    # verbatim reference, when the tree (or the staged copy) exists
+    importlib.reload(refarm)
+    roots = [r for r in refarm._candidates() if os.path.isfile(os.path.join(r, refarm._REL))]
+    if roots:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fn, kind, where = refarm.load_apply()
+        assert kind == "reference" and where.endswith("C_31apply_muti_kernel_to_landsat.py")
+        got = refarm.multi_kernel_pairs(hr, kb, sb, pool, kidx, nidx, 8)
+        assert np.array_equal(got, want)                  # the port issues the same calls: bit-identical here
+
+
+def test_bench_parity_audit_reports_fractions_and_the_two_part_rule():
+    """bench.parity_audit: per regime the maximum, the 99.9th percentile and the FRACTION of pixels over the plain bar."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rs = np.random.RandomState(0)
+    h = 2
+    hs = rs.rand(2 * h, 5, 16, 16).astype(np.float32) * 10.0
+    exact = rs.rand(2 * h, 5, 4, 4) * 10.0
+    rng = (hs.max(axis=(2, 3)) - hs.min(axis=(2, 3)))[:, :, None, None].astype(np.float64)
+    ref = exact.copy()
+    ref[h:] += 1.3e-5 * rng[h:] * np.sign(rs.randn(h, 5, 4, 4))      # a "water" reference 1.3e-5 x range from exact
+    got = exact + 1e-6 * rng
+    a = bench.parity_audit(got.astype(np.float64), ref, exact, hs, h)
+    assert a["textured"]["ours_vs_ref_frac_over_bar"] == 0.0 and a["textured_within_plain_bar"]
+    assert a["water"]["ref_vs_fp64_frac_over_bar"] == 1.0 and a["water"]["ours_vs_fp64_frac_over_bar"] == 0.0
+    assert 0.0 < a["water"]["ours_vs_ref_frac_over_bar"] <= 1.0 and a["two_part_rule_holds"]
+    bad = exact + 2e-5 * rng                                         # ours off by twice the bar: the rule must fail
+    assert not bench.parity_audit(bad, ref, exact, hs, h)["two_part_rule_holds"]
