@@ -308,30 +308,31 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
             }
         }
     };
-    // two row buffers: the next row's LDS.128 are in flight while the current row is multiplied
+    // Two rows per iteration, both loaded at the top: the second row's LDS.128 are in flight while the first row is
+    // multiplied.  Nothing is carried across the back-edge -- a software pipeline that loaded row rr + 2 inside iteration
+    // rr made ptxas copy ~70 registers per iteration at the back-edge (11 % of the issued instructions, ncu r2z).
     {
         u64 PA[G::NPL], PB[G::NPL];
-        load_row(0, PA);
         int rr = 0;
 #pragma unroll 1
         for (; rr < G::FULL0; rr += 2) {
+            load_row(rr, PA);
             load_row(rr + 1, PB);
             mac_partial(rr, PA);
-            load_row(rr + 2, PA);
             mac_partial(rr + 1, PB);
         }
 #pragma unroll 1
         for (; rr < G::KW; rr += 2) {
+            load_row(rr, PA);
             load_row(rr + 1, PB);
             mac_full(rr, PA);
-            if (rr + 2 < G::NR) load_row(rr + 2, PA);
             mac_full(rr + 1, PB);
         }
 #pragma unroll 1
         for (; rr < G::NR; rr += 2) {
+            load_row(rr, PA);
             load_row(rr + 1, PB);
             mac_partial(rr, PA);
-            if (rr + 2 < G::NR) load_row(rr + 2, PA);
             mac_partial(rr + 1, PB);
         }
     }
