@@ -179,12 +179,9 @@ static int degrade_common(const float* hr, int64_t N, int C, int H, int W, int64
     }
     const char* why3 = "";
     const bool reg_ok = reg_shape_ok(a, down_mode, &why3);
-    // factor 2 / 4 (FP32-bound or near the ridge) and 64-wide patches at any factor go to the box-tile kernel; the one
-    // sweep cell where the older register-tile kernel still wins is k = 31 at factor 2 on 64-wide patches (0.60 vs 0.46 of
-    // the FP32 peak, r2j: 230 registers leave the box kernel 7 one-warp CTAs per SM there)
+    // factor 2 / 4 (FP32-bound or near the ridge) and 64-wide patches at any factor go to the box-tile kernel
     const bool band = a.W <= 64 && a.H <= 64;
-    if (algo == KMSR_ALGO_AUTO && box_ok && (a.g.stride <= 4 || band) && a.W >= 48 && a.H >= 48 &&
-        !(band && a.g.kh == 31 && a.g.stride == 2 && reg_ok))
+    if (algo == KMSR_ALGO_AUTO && box_ok && (a.g.stride <= 4 || band) && a.W >= 48 && a.H >= 48)
         return launch_degrade_box(a, st);
     if (algo == KMSR_ALGO_REG) {
         KMSR_REQUIRE(reg_ok, KMSR_E_UNSUPPORTED, "degrade: register-tile kernel does not cover this call (%s)", why3);

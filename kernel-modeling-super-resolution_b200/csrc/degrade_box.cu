@@ -87,6 +87,8 @@ struct BoxArgs {
     int regionF;            // floats per staged region (8 planes; band mode: + the two clamp rows, see clamp_floats)
     int clamp_rows;         // band mode: the two clamp rows are staged
     int replicate, noise_mode;
+    int slot;               // ticket slot of this launch
+    unsigned int ngroups_total;   // groups (CTAs, or warps in band mode) that draw tickets
 };
 
 // Band mode, replicate padding: rows above / below the band clamp to row 0 / H-1.  A lane that clamps would read another
@@ -103,6 +105,15 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+
+// Work distribution in band mode: the warps of persistent CTAs draw their bands from a ticket counter, so the hardware's
+// dynamic balance between SMs is kept (a static stride lost 10 % to SM-to-SM speed differences, r2o) while a warp can
+// fetch its next band's pixels during the epilogue of the current one.  One counter pair per launch slot (the host
+// hands out slots round robin, so launches in flight on different streams do not share one); the last group to finish
+// resets its slot.
+constexpr int kTicketSlots = 64;
+__device__ unsigned int g_box_next[kTicketSlots];
+__device__ unsigned int g_box_done[kTicketSlots];
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
                                             uint32_t bar) {
@@ -137,43 +148,81 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
     }
     __syncthreads();
 
-    // ---- work item ----
-    long long band;
-    int tileX0 = 0, tileY0 = 0;
-    if (BAND) {
-        band = (long long)blockIdx.x * a.groups + warp;
-        if (band >= a.nbands) return;                            // whole warps leave; no CTA-wide barrier follows
-    } else {
-        band = blockIdx.x / a.tiles;
-        const int t = (int)(blockIdx.x - band * a.tiles);
-        const int ty = t / a.tiles_x;
-        tileY0 = 128 * ty; tileX0 = 128 * (t - ty * a.tiles_x);
-    }
-    const long long n = band / a.C;
-    const int c = (int)(band - n * a.C);
-    const int rx0 = tileX0 - G::PADL;                             // HR column of staged column 0
-    const int ry0 = BAND ? 0 : tileY0 - G::PADU;                  // HR row of staged row 0 (a multiple of 8)
-
-    // ---- TMA: one box per row residue j (rows j, j+8, ... of the staged window), 8 lanes issue in parallel ----
+    // ---- work items: tickets (see g_box_next); item -> (band, tile) ----
+    const unsigned int nitems = (unsigned int)(BAND ? a.nbands : a.nbands * a.tiles);
     const bool clamp_rows = BAND && a.clamp_rows;
-    if (BAND || warp == 0) {
-        if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)(a.NQ * a.WB) + (clamp_rows ? 8u * (uint32_t)a.W : 0u));
-        __syncwarp();
-        if (lane < 8)
-            tma_load_5d(smem_u32(region + (size_t)lane * a.planeF), &tmap, rx0, lane, ry0 / 8, c, (int)n, bar);
-        else if (clamp_rows && lane < 10) {
-            const float* band0 = a.hr + n * a.sN + (long long)c * a.sC;
-            const int top = lane == 8;                   // row 0 -> row group 7, row H-1 -> row group 0 of the clamp plane
-            bulk_load(smem_u32(region + (size_t)8 * a.planeF + (top ? clamp_top_offset(a.WB) : 0) + G::PADL),
-                      band0 + (top ? 0 : (long long)(a.H - 1) * a.sH), 4u * (uint32_t)a.W, bar);
+    const bool replicate = a.replicate != 0;
+    const bool noisy = a.noise_mode != KMSR_NOISE_NONE;
+    // thread (ly, lx): outputs of HR rows tileY0 + 8 ly .. +7, HR columns tileX0 + 16 lx .. +15
+    const int lx = BAND ? (lane >> 3) : ((warp & 1) * 4 + (lane >> 3));
+    const int ly = BAND ? (lane & 7) : ((warp >> 1) * 8 + (lane & 7));
+    const float* tbase = region + 16 * lx;
+    unsigned int* ticket_s = reinterpret_cast<unsigned int*>(bsm + 64);      // tile mode: the drawn ticket, broadcast
+    auto group_sync = [&]() {
+        if (BAND) __syncwarp();
+        else __syncthreads();
+    };
+    // one thread of the group draws, everybody learns the result (the latency of the atomic is what the caller hides)
+    auto draw_begin = [&]() -> unsigned int {
+        unsigned int t = 0;
+        if (gtid == 0) t = atomicAdd(&g_box_next[a.slot], 1u);
+        return t;
+    };
+    auto draw_end = [&](unsigned int t) -> unsigned int {
+        if (BAND) return __shfl_sync(0xffffffffu, t, 0);
+        if (gtid == 0) *ticket_s = t;
+        __syncthreads();
+        const unsigned int r = *ticket_s;
+        __syncthreads();
+        return r;
+    };
+    auto finish = [&]() {                                  // the last group resets the slot for a later launch
+        if (gtid == 0) {
+            __threadfence();
+            if (atomicAdd(&g_box_done[a.slot], 1u) == a.ngroups_total - 1) {
+                g_box_next[a.slot] = 0;
+                g_box_done[a.slot] = 0;
+                __threadfence();
+            }
         }
-    }
-
-    // ---- per-band parameters and the composite kernel (shifted by one float when the first tap is odd): cp.async, so
-    // one global-memory latency covers the whole copy (register-returning loads made a lone warp pay it per element)
-    const int kid = a.kidx ? __ldg(a.kidx + n) : 0;
-    {
-        const float* kc = a.comp + ((long long)kid * a.C + c) * (G::KW * a.KWp);
+    };
+    struct Item { long long band, n; int c, tileX0, tileY0; };
+    auto decode = [&](unsigned int it) {
+        Item w;
+        w.tileX0 = 0; w.tileY0 = 0;
+        unsigned int bnd = it;
+        if (!BAND) {
+            bnd = it / (unsigned int)a.tiles;
+            const int t = (int)(it - bnd * (unsigned int)a.tiles);
+            const int ty = t / a.tiles_x;
+            w.tileY0 = 128 * ty; w.tileX0 = 128 * (t - ty * a.tiles_x);
+        }
+        const unsigned int nn = bnd / (unsigned int)a.C;
+        w.band = bnd; w.n = nn;
+        w.c = (int)(bnd - nn * (unsigned int)a.C);
+        return w;
+    };
+    // TMA: one box per row residue j (rows j, j+8, ... of the staged window), 8 lanes issue in parallel; then the
+    // composite kernel of the band (shifted by one float when the first tap is odd) by cp.async, so one global-memory
+    // latency covers the whole copy.  Called for the first item up front and for every later one as soon as the row
+    // loop of the previous item has read its last staged row: the fetch overlaps the epilogue.
+    auto issue = [&](const Item& w) {
+        const int rx0 = w.tileX0 - G::PADL;                        // HR column of staged column 0
+        const int ry0 = BAND ? 0 : w.tileY0 - G::PADU;             // HR row of staged row 0 (a multiple of 8)
+        if (BAND || warp == 0) {
+            if (lane == 0) mbar_arrive_expect_tx(bar, 32u * (uint32_t)(a.NQ * a.WB) + (clamp_rows ? 8u * (uint32_t)a.W : 0u));
+            __syncwarp();
+            if (lane < 8)
+                tma_load_5d(smem_u32(region + (size_t)lane * a.planeF), &tmap, rx0, lane, ry0 / 8, w.c, (int)w.n, bar);
+            else if (clamp_rows && lane < 10) {
+                const float* band0 = a.hr + w.n * a.sN + (long long)w.c * a.sC;
+                const int top = lane == 8;               // row 0 -> bank offset of row group 7, row H-1 -> that of row group 0
+                bulk_load(smem_u32(region + (size_t)8 * a.planeF + (top ? clamp_top_offset(a.WB) : 0) + G::PADL),
+                          band0 + (top ? 0 : (long long)(a.H - 1) * a.sH), 4u * (uint32_t)a.W, bar);
+            }
+        }
+        const int kid = a.kidx ? __ldg(a.kidx + w.n) : 0;
+        const float* kc = a.comp + ((long long)kid * a.C + w.c) * (G::KW * a.KWp);
         const uint32_t wdst = smem_u32(wsm);
         if (!G::ODD && a.KWp == G::WP) {
             for (int e = gtid; e < G::KW * G::WP / 4; e += gthreads)
@@ -188,26 +237,37 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    const bool noisy = a.noise_mode != KMSR_NOISE_NONE;
+    };
+
+    // Band mode is persistent (every warp draws bands until none is left: +2-7 %, r2t); tile mode is not -- one tile per
+    // CTA, the hardware schedules: with tickets the four warps of a tile rendezvous before the epilogue and the kernel
+    // measured 3-7 % slower at factor 2 / 4 (r2t; 9-12 % with a static stride, r2o).
+    constexpr bool PERSIST = BAND;
+    unsigned int item = PERSIST ? draw_end(draw_begin()) : blockIdx.x;
+    if (PERSIST && item >= nitems) { finish(); return; }         // uniform over the group
+    Item cur = decode(item);
+    issue(cur);
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (;;) {
+    const unsigned int next_raw = PERSIST ? draw_begin() : 0u;    // the ticket of the item after this one: in flight during the rows
+    const long long band = cur.band, n = cur.n;
+    const int c = cur.c, tileX0 = cur.tileX0, tileY0 = cur.tileY0;
+    const int rx0 = tileX0 - G::PADL;
+    const int ry0 = BAND ? 0 : tileY0 - G::PADU;
+    const int kid = a.kidx ? __ldg(a.kidx + n) : 0;
     const float ds = __ldg(a.dsum + (long long)kid * a.C + c);
     const float scale = a.noise_mode == KMSR_NOISE_SIGMA ? __ldg(a.sigma + (long long)kid * a.C + c) : 1.0f;
     const int nid = noisy ? __ldg(a.nidx + n) : 0;
-
-    // thread (ly, lx): outputs of HR rows tileY0 + 8 ly .. +7, HR columns tileX0 + 16 lx .. +15
-    const int lx = BAND ? (lane >> 3) : ((warp & 1) * 4 + (lane >> 3));
-    const int ly = BAND ? (lane & 7) : ((warp >> 1) * 8 + (lane & 7));
     const int hy0 = tileY0 + 8 * ly - G::PAD;                     // HR row of the thread's input row 0
     const int colsLeft = a.W - (tileX0 + 16 * lx);                // image columns from the thread's first column on
-    const bool replicate = a.replicate != 0;
     const bool ledge = replicate && tileX0 + 16 * lx == 0;        // halo columns left of the band in this thread's segment
     const bool redge = replicate && colsLeft == 16;               // ... right of the band (W % 16 == 0: box_shape_ok)
-    const float* tbase = region + 16 * lx;
 
     asm volatile("cp.async.wait_all;" ::: "memory");
-    if (BAND) __syncwarp();
-    else __syncthreads();                                         // composite kernel staged
-    mbar_wait(bar, 0);
+    group_sync();                                                 // composite kernel staged
+    mbar_wait(bar, phase);
+    phase ^= 1;
 
     // pivot: the thread's own first pixel, clamped into the image
     float pv;
@@ -337,6 +397,16 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
         }
     }
 
+    // ---- every warp of the group has read its last staged row: fetch the next item while this one is written out ----
+    const unsigned int next_item = PERSIST ? draw_end(next_raw) : nitems;
+    if (PERSIST) group_sync();
+    const bool has_next = PERSIST && next_item < nitems;
+    Item nxt = cur;
+    if (has_next) {
+        nxt = decode(next_item);
+        issue(nxt);
+    }
+
     // ---- epilogue: even + odd taps, pivot back, noise, store ----
     const long long ohw = (long long)a.Ho * a.Wo;
     float* outb = a.lr + band * ohw;
@@ -382,6 +452,11 @@ degrade_box_kernel(const __grid_constant__ CUtensorMap tmap, const BoxArgs a) {
                 if (Xb + x < a.Wo) o[x] = noisy ? fmaf(scale, __ldg(z + x), res[x]) : res[x];
         }
     }
+    if (!has_next) break;
+    cur = nxt;
+    item = next_item;
+    }   // ticket loop
+    if (PERSIST) finish();
 }
 
 template <int K, int S>
@@ -458,18 +533,32 @@ int launch_box(const DegradeArgs& a, cudaStream_t st) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "degrade (box): cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
 
-    const long long grid = band_mode ? (t.nbands + t.groups - 1) / t.groups : t.nbands * t.tiles;
-    KMSR_REQUIRE(grid < (1ll << 31), KMSR_E_INVALID, "degrade (box): too many tiles");
+    // band mode: persistent CTAs, as many as are resident at once; bands come from the ticket counter of this launch's slot
+    int sms = 0;
+    KMSR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long nitems = band_mode ? t.nbands : t.nbands * t.tiles;
+    KMSR_REQUIRE(nitems < (1ll << 31), KMSR_E_INVALID, "degrade (box): too many tiles");
+    const long long work_ctas = band_mode ? (t.nbands + t.groups - 1) / t.groups : nitems;
+    static std::atomic<unsigned int> launch_seq{0};
+    t.slot = (int)(launch_seq.fetch_add(1, std::memory_order_relaxed) % kTicketSlots);
     set_algo("box");
+    int per_sm = 0;
+    long long grid = 0;
     if (band_mode) {
         auto kern = degrade_box_kernel<K, S, true>;
         KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        KMSR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * t.groups, smem));
+        const long long resident = (long long)sms * (per_sm > 0 ? per_sm : 1);
+        grid = work_ctas < resident ? work_ctas : resident;
+        t.ngroups_total = (unsigned int)(grid * t.groups);
         kern<<<(unsigned)grid, 32 * t.groups, smem, st>>>(tmap, t);
     } else {
         auto kern = degrade_box_kernel<K, S, false>;
         KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        grid = work_ctas;                                            // one tile per CTA
+        t.ngroups_total = (unsigned int)grid;
         kern<<<(unsigned)grid, kBoxThreads, smem, st>>>(tmap, t);
     }
     KMSR_LAUNCH_CHECK("degrade_box_kernel");
