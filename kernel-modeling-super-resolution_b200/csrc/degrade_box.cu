@@ -25,8 +25,9 @@
 // Kernels with an odd halo (k = 11, 15, 31) put their first tap on an odd column: the first and the last tap of a row
 // are issued as scalar FFMA on one half of the accumulator pair and the k + S - 3 taps between them as aligned FFMA2
 // pairs (same FMA-pipe time as an even halo, no zero tap multiplied with a real pixel).
-// Non-persistent: one CTA of 128 threads per tile, or of 1-4 warps with one band each; as many CTAs per SM as shared
-// memory holds (2 in tile mode); a CTA's TMA wait overlaps the other CTAs' arithmetic.
+// Tile mode: one CTA of 128 threads per tile, two CTAs per SM (shared memory), the hardware schedules; a CTA's TMA wait
+// overlaps the other CTA's arithmetic.  Band mode: persistent CTAs of 1-4 warps, every warp draws whole bands from a
+// ticket counter and issues the next band's TMA before it writes the current one out.
 #include <cuda.h>
 #include <stdlib.h>
 
