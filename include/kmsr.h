@@ -62,7 +62,9 @@ enum {
 };
 /* algo: kernel selection for kmsr_degrade_* */
 enum {
-    KMSR_ALGO_AUTO = 0,    /* headline TMA kernel, else the generic streaming kernel, else the tiled kernel */
+    KMSR_ALGO_AUTO = 0,    /* the fastest kernel that covers the call: TMA (headline shape), BOX (factor 2 / 4 and
+                              patches of at most 64 x 64), STREAM (the other box-mean calls with k in 11..31 at factor 8),
+                              REG (what BOX refuses), TILED (everything else); kmsr_last_algo() says which ran          */
     KMSR_ALGO_TILED = 1,   /* polyphase shared-memory tile kernel (any k, factor, H, W, pad / down mode)   */
     KMSR_ALGO_TMA = 2,     /* headline TMA row-streaming kernel (k = 13, factor 8, W a multiple of 256, H % 8 == 0,
                               H <= 512); KMSR_E_UNSUPPORTED if the shape does not qualify                      */
