@@ -210,3 +210,19 @@ def list_patch_files(directory: str, sort: bool, exts=PATCH_EXTS) -> list:
     (D:71, E:208 -- the order the reference's RNG draws are bound to)."""
     names = [f for f in os.listdir(directory) if f.endswith(exts)]
     return sorted(names) if sort else names
+
+
+if __name__ == "__main__":
+    # python -m kmsr_b200.patch_io nc2npz <in.nc|dir> <out.npz|dir>   (or npz2nc); needs the netCDF4 module
+    import sys
+    if len(sys.argv) != 4 or sys.argv[1] not in ("nc2npz", "npz2nc"):
+        raise SystemExit("usage: python -m kmsr_b200.patch_io nc2npz|npz2nc <file or folder> <file or folder>")
+    fn, ext_in, ext_out = (nc_to_npz, ".nc", ".npz") if sys.argv[1] == "nc2npz" else (npz_to_nc, ".npz", ".nc")
+    src, dst = sys.argv[2], sys.argv[3]
+    if os.path.isdir(src):
+        os.makedirs(dst, exist_ok=True)
+        for name in sorted(os.listdir(src)):
+            if name.endswith(ext_in):
+                fn(os.path.join(src, name), os.path.join(dst, name[:-len(ext_in)] + ext_out))
+    else:
+        fn(src, dst)

@@ -240,6 +240,48 @@ def test_patch_io_roundtrip_and_listing(tmp_path):
             pio.read_group_bands(str(tmp_path / "z.nc"), "denoised")
 
 
+@pytest.mark.parametrize("backend", ["netCDF4", "fake"])
+def test_nc_files_round_trip(tmp_path, backend, monkeypatch):
+    """f3: the NetCDF4 branch of patch_io (E_make_train_data.py:84-117 layout: groups hr / lr with one zlib f4 variable
+    per band on dims (y, x), navigation_data with per-variable dims) read back with the reference's own reader calls,
+    and the documented .nc -> .npz -> .nc conversion.  "netCDF4" runs against the real module and is skipped where it
+    is absent (this image); "fake" runs the same call sequence against tests/fake_netcdf4.py, which keeps libnetcdf's
+    structural checks (dimensions exist and match, no duplicate names, append needs the file)."""
+    if backend == "netCDF4":
+        netCDF4 = pytest.importorskip("netCDF4")
+    else:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import fake_netcdf4 as netCDF4
+        monkeypatch.setitem(sys.modules, "netCDF4", netCDF4)
+    from kmsr_b200 import BAND_NAMES, patch_io as pio
+    rs = np.random.RandomState(3)
+    hr = rs.rand(5, 16, 16).astype(np.float32) * 80
+    lr = hr[:, ::8, ::8].copy()
+    nav = {"latitude": rs.rand(16, 16).astype(np.float32), "longitude": rs.rand(16, 16).astype(np.float32)}
+    p = str(tmp_path / "pair.nc")
+    pio.write_training_sample(p, hr, lr, nav)
+    with netCDF4.Dataset(p, "r") as ds:                                  # as E:33-58 / a training loader reads it
+        assert set(ds.groups) == {"hr", "lr", "navigation_data"}
+        for g, arr in (("hr", hr), ("lr", lr)):
+            for i, b in enumerate(BAND_NAMES):
+                var = ds.groups[g].variables[b]
+                assert var.dtype == np.float32 and var.dimensions == ("y", "x") and var.filters()["zlib"]
+                assert np.array_equal(np.asarray(var[:]), arr[i])
+        assert np.array_equal(np.asarray(ds.groups["navigation_data"].variables["latitude"][:]), nav["latitude"])
+    z = str(tmp_path / "pair.npz")
+    pio.nc_to_npz(p, z)
+    assert np.array_equal(pio.read_group_bands(z, "hr"), hr) and np.array_equal(pio.read_group_bands(z, "lr"), lr)
+    assert np.array_equal(pio.read_navigation(z)["longitude"], nav["longitude"])
+    back = str(tmp_path / "back.nc")
+    pio.npz_to_nc(z, back)
+    assert np.array_equal(pio.read_group_bands(back, "hr"), hr) and np.array_equal(pio.read_group_bands(back, "lr"), lr)
+    assert np.array_equal(pio.read_navigation(back)["latitude"], nav["latitude"])
+    # C_30:171-196 style append: copy, then add a group to the copy
+    q = str(tmp_path / "pair_blurred.nc")
+    pio.add_group(q, "blurred", lr, src=back, history="blurred with kernel_0", long_name="Blurred radiance at {wl} nm")
+    assert np.array_equal(pio.read_group_bands(q, "blurred"), lr) and np.array_equal(pio.read_group_bands(q, "hr"), hr)
+
+
 def test_selector_logits_match_the_reference_model(golden, synth):
     """f2: SelectorNet inference (train_gemini.py:14-39, eval mode) from the shipped moe_model.pth weights against the
     logits the reference module produced (tests/golden/make_selector_golden.py); hard pick = argmax."""
