@@ -20,7 +20,7 @@ tot = collections.Counter()
 for f in sorted(funcs, key=lambda f: f.split("\n")[0]):
     name = f.split("\n")[0].strip()
     dem = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip() or name
-    dem = re.sub(r"\(anonymous namespace\)::", "", dem.split("(")[0]).replace("void kmsr::", "")
+    dem = re.sub(r"\(anonymous namespace\)::", "", dem).split("(")[0].replace("void ", "").replace("kmsr::", "")
     ops = collections.Counter(re.findall(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", f, re.M))
     n = sum(ops.values())
     def cnt(k):
