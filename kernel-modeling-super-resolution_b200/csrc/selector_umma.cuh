@@ -1,0 +1,395 @@
+// selector_umma.cuh -- SelectorNet convolutions (muti_kernel/train_gemini.py:14-39) on the 5th-generation tensor cores:
+// `tcgen05.mma.kind::tf32` with the accumulators in tensor memory, SURVEY.md 8f row f2, round 2.
+//
+// A 3x3 / stride-2 / pad-1 convolution is the GEMM  D[pixel, cout] = sum_k A[pixel, k] B[cout, k],  k = (tap, cin).
+// One MMA tile is 128 output pixels (raster order inside a patch) x COUT channels; K is walked in stages of 16 (two MMA
+// k-steps of 8).  fp32-level accuracy comes from the 3xTF32 split, arranged so that two MMAs do the work of three:
+//     D[:, 0:2C]  += A_hi x [B_hi ; B_lo]^T      (N = 2 COUT: hi*hi in columns 0..C-1, hi*lo in columns C..2C-1)
+//     D[:, 0:C]   += A_lo x  B_hi^T              (N = COUT, accumulated onto the hi*hi columns)
+// and the epilogue adds the two column halves.  Both operands sit in shared memory in the K-major canonical layout
+// without swizzle (core matrix = 8 rows x 16 bytes, contiguous), which is what lets plain threads build the im2col
+// operand: a 16-byte chunk = 4 consecutive input channels of one tap of one output pixel (channel-last activations).
+//
+// Warp roles (416 threads, one persistent CTA per SM):
+//   warps 0-3   epilogue: tcgen05.ld of the tile (TMEM lane quadrant = warp), halves added, + bias, ReLU, then either
+//               the channel-last store or -- last layer -- the per-tile channel sums (shuffle reduce-scatter, fixed
+//               order, deterministic) that pool_fc_kernel turns into logits
+//   warp  4     one thread issues the MMAs and the commits that release a ring slot / publish an accumulator buffer
+//   warps 5-12  builders: global (L2) -> registers -> TF32 hi / lo split -> canonical operand tiles in a 4-slot ring; loads
+//               run two stages ahead of the stores (register ring of three); one of them streams the stage's weights, already
+//               laid out as the shared-memory image by the host, with one bulk copy
+// A pass = two M tiles sharing every weight stage; accumulators are double-buffered in TMEM when 8 COUT <= 512 columns.
+#pragma once
+#include "common.cuh"
+#include "tma_util.cuh"
+
+namespace kmsr {
+namespace umma {
+
+constexpr int kEpiWarps = 4, kBuildWarps = 8;
+constexpr int kBuildThreads = 32 * kBuildWarps;
+constexpr int kBuild0 = 32 * (kEpiWarps + 1);                  // first builder thread
+constexpr int kThreads = kBuild0 + kBuildThreads;              // 416
+constexpr int kSlots = 4;                                      // operand ring
+constexpr int kTPP = 2;                                        // M tiles per pass
+constexpr uint32_t kTileBytes = 8192;                          // one 128 x 16 fp32 operand tile: [4 chunks][16 groups][8 rows][16 B]
+constexpr uint32_t kChunkBytes = 2048;                         // LBO of the A tiles (core matrices adjacent in K)
+
+struct ConvUArgs {
+    const float* in;        // first layer: [N, 5, H, W]; others: [N, H, W, CIN] (channel-last)
+    const float* wst;       // [stage][4 chunks][2 COUT / 8][8][4]: shared-memory image of [B_hi ; B_lo] per stage (host-prepared)
+    const float* bias;      // [COUT]
+    float* out;             // [N, Ho, Wo, COUT] channel-last, or nullptr when pooling
+    float* pool_part;       // [N, tiles, COUT] per-tile channel sums (last layer), or nullptr
+    int H, W, Ho, Wo;
+    int tiles;              // Ho Wo / 128, even
+    long long passes;       // N tiles / 2
+};
+
+__device__ __forceinline__ uint32_t tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+// shared-memory matrix descriptor, K-major, no swizzle: start address, LBO (K direction), SBO (M / N direction), version 1
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+                 "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(float (&v)[16], uint32_t taddr) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// one stage of the butterfly reduce-scatter over the lanes of a warp: 2 H live values per lane become H
+template <int H>
+__device__ __forceinline__ void rs_stage(float (&v)[32], int lane) {
+    const bool up = (lane & H) != 0;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float send = up ? v[j] : v[j + H];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, H);
+        v[j] = (up ? v[j + H] : v[j]) + recv;
+    }
+}
+
+template <int CIN, int COUT>
+struct Shape {
+    static constexpr int G = CIN >= 16 ? CIN / 16 : 1;                 // channel groups of 16 per tap
+    static constexpr int S = CIN == 5 ? 3 : 9 * G;                     // stages per pass (first layer: K = 45 -> 48)
+    static constexpr uint32_t A_BYTES = kTPP * 2 * kTileBytes;         // hi and lo tiles of both M tiles
+    static constexpr uint32_t B_LBO = 32u * COUT;                      // (2 COUT / 8) row groups x 128 B
+    static constexpr uint32_t B_BYTES = 4 * B_LBO;
+    static constexpr uint32_t SLOT = A_BYTES + B_BYTES;
+    static constexpr int NBUF = 8 * COUT <= 512 ? 2 : 1;               // accumulator buffers in TMEM
+    static constexpr int TCOLS = 2 * COUT * kTPP;                      // columns per buffer
+    static constexpr size_t SMEM = (size_t)kSlots * SLOT + 256 /* barriers */ + COUT * 4 + 4 * 128 * 4 + 1024 /* alignment */;
+    static_assert(S % 3 == 0, "the builder's register ring is unrolled by three");
+};
+
+template <int CIN, int COUT, bool POOL>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const ConvUArgs a) {
+    using Sh = Shape<CIN, COUT>;
+    constexpr int S = Sh::S, G = Sh::G;
+    extern __shared__ uint8_t umma_smem_raw[];
+    const uint32_t raw = smem_u32(umma_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* basep = umma_smem_raw + (base - raw);
+    const uint32_t bars = base + kSlots * Sh::SLOT;                    // full[4] empty[4] tfull[2] tempty[2] | tmem holder
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 32u + 8u * s; };
+    auto tfull_bar = [&](int b) { return bars + 64u + 8u * b; };
+    auto tempty_bar = [&](int b) { return bars + 80u + 8u * b; };
+    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(basep + kSlots * Sh::SLOT + 96);
+    float* bias_s = reinterpret_cast<float*>(basep + kSlots * Sh::SLOT + 256);
+    float* red_s = bias_s + COUT;                                      // [4 warps][128] (pooling only)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(full_bar(s), kBuildThreads + 1);                 // every builder after its stores + the weight copy's expect_tx
+            mbar_init(empty_bar(s), 1);                                // one tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 32 * kEpiWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int c = tid; c < COUT; c += kThreads) bias_s[c] = a.bias[c];
+    if (warp == kEpiWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_holder)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *tmem_holder;
+    const int half_tiles = a.tiles / kTPP;
+
+    if (warp < kEpiWarps) {
+        // ------------------------------------------------------------------------------------------ epilogue
+        const int row = tid;                                           // row of the M tile = TMEM lane
+        const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
+        uint32_t pc = 0;
+        for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
+            const int buf = (int)(pc % Sh::NBUF);
+            const long long n = pass / half_tiles;
+            const int tile0 = (int)(pass - n * half_tiles) * kTPP;
+            mbar_wait(tfull_bar(buf), (pc / Sh::NBUF) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int t = 0; t < kTPP; ++t) {
+                const uint32_t tcol = lane_addr + (uint32_t)(buf * Sh::TCOLS + t * 2 * COUT);
+                if constexpr (!POOL) {
+                    float* dst = a.out + (((long long)n * a.tiles + tile0 + t) * 128 + row) * COUT;
+#pragma unroll 1
+                    for (int j0 = 0; j0 < COUT; j0 += 16) {
+                        float p[16], q[16];
+                        tmem_ld16(p, tcol + j0);
+                        tmem_ld16(q, tcol + COUT + j0);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 o;
+                            o.x = fmaxf(p[j] + q[j] + bias_s[j0 + j], 0.0f);
+                            o.y = fmaxf(p[j + 1] + q[j + 1] + bias_s[j0 + j + 1], 0.0f);
+                            o.z = fmaxf(p[j + 2] + q[j + 2] + bias_s[j0 + j + 2], 0.0f);
+                            o.w = fmaxf(p[j + 3] + q[j + 3] + bias_s[j0 + j + 3], 0.0f);
+                            *reinterpret_cast<float4*>(dst + j0 + j) = o;
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j0 = 0; j0 < COUT; j0 += 32) {
+                        float v[32];
+                        {
+                            float p[16], q[16];
+                            tmem_ld16(p, tcol + j0);
+                            tmem_ld16(q, tcol + COUT + j0);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(p[j] + q[j] + bias_s[j0 + j], 0.0f);
+                            tmem_ld16(p, tcol + j0 + 16);
+                            tmem_ld16(q, tcol + COUT + j0 + 16);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[16 + j] = fmaxf(p[j] + q[j] + bias_s[j0 + 16 + j], 0.0f);
+                        }
+                        rs_stage<16>(v, lane);
+                        rs_stage<8>(v, lane);
+                        rs_stage<4>(v, lane);
+                        rs_stage<2>(v, lane);
+                        rs_stage<1>(v, lane);
+                        red_s[warp * 128 + j0 + lane] = v[0];         // column j0 + lane, summed over this warp's 32 pixels
+                    }
+                    if (t == kTPP - 1) {                                 // every TMEM read of the pass is done: hand the buffer back
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(buf));
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    for (int c = tid; c < COUT; c += 128)
+                        a.pool_part[((long long)n * a.tiles + tile0 + t) * COUT + c] =
+                            ((red_s[c] + red_s[128 + c]) + red_s[256 + c]) + red_s[384 + c];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
+            if constexpr (!POOL) {
+                tc_fence_before();
+                mbar_arrive(tempty_bar(buf));
+            }
+        }
+    } else if (warp == kEpiWarps) {
+        // ------------------------------------------------------------------------------------------ MMA issue
+        if (lane == 0) {
+            constexpr uint32_t idesc_cat = idesc_tf32(2 * COUT), idesc_one = idesc_tf32(COUT);
+            uint32_t it = 0, pc = 0;
+            for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
+                const int buf = (int)(pc % Sh::NBUF);
+                mbar_wait(tempty_bar(buf), ((pc / Sh::NBUF) & 1u) ^ 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int s = 0; s < S; ++s, ++it) {
+                    const int slot = (int)(it % kSlots);
+                    mbar_wait(full_bar(slot), (it / kSlots) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa = base + slot * Sh::SLOT, sb = sa + Sh::A_BYTES;
+#pragma unroll
+                    for (int t = 0; t < kTPP; ++t) {
+                        const uint32_t dcol = tm + (uint32_t)(buf * Sh::TCOLS + t * 2 * COUT);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint64_t bd = smem_desc(sb + j * 2 * Sh::B_LBO, Sh::B_LBO, 128);
+                            const uint64_t ahi = smem_desc(sa + (t * 2 + 0) * kTileBytes + j * 2 * kChunkBytes, kChunkBytes, 128);
+                            const uint64_t alo = smem_desc(sa + (t * 2 + 1) * kTileBytes + j * 2 * kChunkBytes, kChunkBytes, 128);
+                            mma_tf32_ss(dcol, ahi, bd, idesc_cat, (s | j) != 0);
+                            mma_tf32_ss(dcol, alo, bd, idesc_one, 1u);
+                        }
+                    }
+                    mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot
+                }
+                mma_commit(tfull_bar(buf));                            // ... and once the accumulators are final
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------ operand builders
+        const int bt = tid - kBuild0, bw = bt >> 5;
+        // what a thread loads per stage
+        //   layers 2 / 3: four 16-byte chunks: rows R_i = 64 i + 8 bw + (lane & 7) of the pass, chunk c = lane >> 3
+        //   first layer:  its own row R = bt (16 scalars per stage: k = 16 s + 4 c + e -> (band, dy, dx))
+        constexpr int NV = CIN == 5 ? 4 : 4;
+        float4 rb[3][NV];
+        long long lpass = blockIdx.x;                                  // pass whose stages are being loaded
+        int ls = 0;                                                    // next stage of lpass to load
+        const float* src[4];                                           // layers 2 / 3: pixel (2 oy - 1, 2 ox - 1) + chunk, per row
+        uint32_t edge = 0;                                             // bit 2 i: row i at oy == 0, bit 2 i + 1: ox == 0
+        const float* src1 = nullptr;                                   // first layer: band 0, pixel (2 oy - 1, 2 ox - 1)
+        auto set_pass = [&](long long pass) {
+            const long long n = pass / half_tiles;
+            const int tile0 = (int)(pass - n * half_tiles) * kTPP;
+            if constexpr (CIN == 5) {
+                const int P = tile0 * 128 + bt;
+                const int oy = P / a.Wo, ox = P - oy * a.Wo;
+                src1 = a.in + (long long)n * 5 * a.H * a.W + (long long)(2 * oy - 1) * a.W + (2 * ox - 1);
+                edge = (oy == 0 ? 1u : 0u) | (ox == 0 ? 2u : 0u);
+            } else {
+                edge = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int P = tile0 * 128 + 64 * i + 8 * bw + (lane & 7);
+                    const int oy = P / a.Wo, ox = P - oy * a.Wo;
+                    src[i] = a.in + (((long long)n * a.H + (2 * oy - 1)) * a.W + (2 * ox - 1)) * CIN + 4 * (lane >> 3);
+                    edge |= (oy == 0 ? 1u : 0u) << (2 * i) | (ox == 0 ? 2u : 0u) << (2 * i);
+                }
+            }
+        };
+        auto load_stage = [&](int s, float4 (&dst)[NV]) {
+            if constexpr (CIN == 5) {
+                float v[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int k = 16 * s + e;                          // compile-time after unrolling (s is u-derived)
+                    const int ch = k / 9, dy = (k % 9) / 3, dx = k % 3;
+                    const bool ok = k < 45 && !((dy == 0) && (edge & 1u)) && !((dx == 0) && (edge & 2u));
+                    v[e] = ok ? __ldg(src1 + ((long long)ch * a.H + dy) * a.W + dx) : 0.0f;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            } else {
+                const int tap = s / G, g = s - tap * G;
+                const int dy = tap / 3, dx = tap - 3 * dy;
+                const long long off = ((long long)dy * a.W + dx) * CIN + 16 * g;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool ok = !((dy == 0) && ((edge >> (2 * i)) & 1u)) && !((dx == 0) && ((edge >> (2 * i + 1)) & 1u));
+                    dst[i] = ok ? __ldg(reinterpret_cast<const float4*>(src[i] + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        // where they go inside a slot: tile t, part p (hi / lo), chunk c, row r -> (2 t + p) 8192 + 2048 c + 128 (r / 8) + 16 (r % 8)
+        uint32_t dsto[4];
+        if constexpr (CIN == 5) {
+            const int t = bt >> 7, r = bt & 127;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dsto[c] = (2 * t) * kTileBytes + c * kChunkBytes + (r >> 3) * 128 + (r & 7) * 16;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                dsto[i] = (2 * (i >> 1)) * kTileBytes + (lane >> 3) * kChunkBytes + ((i & 1) * 8 + bw) * 128 + (lane & 7) * 16;
+        }
+        auto store_stage = [&](uint32_t slot_base, const float4 (&v)[NV]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t h0 = tf32_rna(v[i].x), h1 = tf32_rna(v[i].y), h2 = tf32_rna(v[i].z), h3 = tf32_rna(v[i].w);
+                st_shared_v4(slot_base + dsto[i], h0, h1, h2, h3);
+                st_shared_v4(slot_base + dsto[i] + kTileBytes, tf32_rna(v[i].x - __uint_as_float(h0)),
+                             tf32_rna(v[i].y - __uint_as_float(h1)), tf32_rna(v[i].z - __uint_as_float(h2)),
+                             tf32_rna(v[i].w - __uint_as_float(h3)));
+            }
+        };
+
+        if (lpass < a.passes) {
+            set_pass(lpass);
+            load_stage(0, rb[0]);
+            load_stage(1, rb[1]);
+        }
+        ls = 2;
+        uint32_t it = 0;
+        for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x) {
+#pragma unroll 1
+            for (int s0 = 0; s0 < S; s0 += 3) {
+#pragma unroll
+                for (int u = 0; u < 3; ++u, ++it) {
+                    // loads of the stage two ahead (possibly of the next pass)
+                    if (ls == S) {
+                        ls = 0;
+                        lpass += gridDim.x;
+                        if (lpass < a.passes) set_pass(lpass);
+                    }
+                    if (lpass < a.passes) load_stage(CIN == 5 ? (u + 2) % 3 : ls, rb[(u + 2) % 3]);
+                    ++ls;
+                    const int slot = (int)(it % kSlots);
+                    const uint32_t sa = base + slot * Sh::SLOT;
+                    mbar_wait(empty_bar(slot), ((it / kSlots) & 1u) ^ 1u);
+                    if (bt == 0) {
+                        mbar_arrive_expect_tx(full_bar(slot), Sh::B_BYTES);
+                        bulk_g2s(sa + Sh::A_BYTES, a.wst + (size_t)(s0 + u) * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
+                    }
+                    store_stage(sa, rb[u]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
+                    mbar_arrive(full_bar(slot));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kEpiWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
+}
+
+template <int CIN, int COUT, bool POOL>
+int launch_conv_umma(const ConvUArgs& a, int sms, cudaStream_t st) {
+    using Sh = Shape<CIN, COUT>;
+    auto kern = conv_umma_kernel<CIN, COUT, POOL>;
+    KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::SMEM));
+    const unsigned grid = (unsigned)(a.passes < sms ? a.passes : sms);
+    kern<<<grid, kThreads, Sh::SMEM, st>>>(a);
+    KMSR_LAUNCH_CHECK("conv_umma_kernel");
+    return KMSR_OK;
+}
+
+}  // namespace umma
+}  // namespace kmsr
