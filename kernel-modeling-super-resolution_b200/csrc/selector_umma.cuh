@@ -20,16 +20,23 @@
 //               laid out as the shared-memory image by the host, with one bulk copy
 // A pass = two M tiles sharing every weight stage; accumulators are double-buffered in TMEM when 8 COUT <= 512 columns.
 #pragma once
+#include <string.h>
+
 #include "common.cuh"
 #include "tma_util.cuh"
+
+#ifndef UMMA_DBG
+#define UMMA_DBG 0      // measurement builds only (scratch/conv_umma_test.cu): 1 no MMA issue, 2 no operand build, 4 no weight copy
+#endif
 
 namespace kmsr {
 namespace umma {
 
 constexpr int kEpiWarps = 4, kBuildWarps = 8;
 constexpr int kBuildThreads = 32 * kBuildWarps;
-constexpr int kBuild0 = 32 * (kEpiWarps + 1);                  // first builder thread
-constexpr int kThreads = kBuild0 + kBuildThreads;              // 416
+constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1;
+constexpr int kBuild0 = 32 * (kEpiWarps + 2);                  // first builder thread
+constexpr int kThreads = kBuild0 + kBuildThreads;              // 448
 constexpr int kSlots = 4;                                      // operand ring
 constexpr int kTPP = 2;                                        // M tiles per pass
 constexpr uint32_t kTileBytes = 8192;                          // one 128 x 16 fp32 operand tile: [4 chunks][16 groups][8 rows][16 B]
@@ -58,6 +65,17 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
+    return d;
+}
+// the same for the 64-byte swizzle (rows of 64 bytes = 16 values of K, 8-row atoms of 512 bytes; what a TMA box with
+// CU_TENSOR_MAP_SWIZZLE_64B writes): LBO is not used (1), SBO = 512, layout type 4 in bits 61-63
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
     return d;
 }
 // instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128
@@ -116,20 +134,21 @@ struct Shape {
     static constexpr int NBUF = 8 * COUT <= 512 ? 2 : 1;               // accumulator buffers in TMEM
     static constexpr int TCOLS = 2 * COUT * kTPP;                      // columns per buffer
     static constexpr size_t SMEM = (size_t)kSlots * SLOT + 256 /* barriers */ + COUT * 4 + 4 * 128 * 4 + 1024 /* alignment */;
-    static_assert(S % 3 == 0, "the builder's register ring is unrolled by three");
 };
 
 template <int CIN, int COUT, bool POOL>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_umma_kernel(const ConvUArgs a) {
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const ConvUArgs a) {
     using Sh = Shape<CIN, COUT>;
+    constexpr bool TMA = CIN != 5;                                     // channel-last input: the hi operand is a TMA box
     constexpr int S = Sh::S, G = Sh::G;
     extern __shared__ uint8_t umma_smem_raw[];
     const uint32_t raw = smem_u32(umma_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* basep = umma_smem_raw + (base - raw);
-    const uint32_t bars = base + kSlots * Sh::SLOT;                    // full[4] empty[4] tfull[2] tempty[2] | tmem holder
+    const uint32_t bars = base + kSlots * Sh::SLOT;                    // full[4] empty[4] tfull[2] tempty[2] | tmem holder | lofull[4]
     auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto lofull_bar = [&](int s) { return bars + 128u + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 32u + 8u * s; };
     auto tfull_bar = [&](int b) { return bars + 64u + 8u * b; };
     auto tempty_bar = [&](int b) { return bars + 80u + 8u * b; };
@@ -140,7 +159,9 @@ conv_umma_kernel(const ConvUArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < kSlots; ++s) {
-            mbar_init(full_bar(s), kBuildThreads + 1);                 // every builder after its stores + the weight copy's expect_tx
+            // first layer: the slot's builder group after its stores + the weight copy's expect_tx; others: the producer's expect_tx
+            mbar_init(full_bar(s), TMA ? 1 : kBuildThreads / kSlots + 1);
+            mbar_init(lofull_bar(s), kBuildThreads);                   // every builder after its lo stores
             mbar_init(empty_bar(s), 1);                                // one tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
@@ -150,7 +171,7 @@ conv_umma_kernel(const ConvUArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int c = tid; c < COUT; c += kThreads) bias_s[c] = a.bias[c];
-    if (warp == kEpiWarps) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_holder)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -232,7 +253,7 @@ conv_umma_kernel(const ConvUArgs a) {
                 mbar_arrive(tempty_bar(buf));
             }
         }
-    } else if (warp == kEpiWarps) {
+    } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------------------------------------ MMA issue
         if (lane == 0) {
             constexpr uint32_t idesc_cat = idesc_tf32(2 * COUT), idesc_one = idesc_tf32(COUT);
@@ -245,6 +266,7 @@ conv_umma_kernel(const ConvUArgs a) {
                 for (int s = 0; s < S; ++s, ++it) {
                     const int slot = (int)(it % kSlots);
                     mbar_wait(full_bar(slot), (it / kSlots) & 1u);
+                    if constexpr (TMA) mbar_wait(lofull_bar(slot), (it / kSlots) & 1u);
                     tc_fence_after();
                     const uint32_t sa = base + slot * Sh::SLOT, sb = sa + Sh::A_BYTES;
 #pragma unroll
@@ -253,10 +275,14 @@ conv_umma_kernel(const ConvUArgs a) {
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const uint64_t bd = smem_desc(sb + j * 2 * Sh::B_LBO, Sh::B_LBO, 128);
-                            const uint64_t ahi = smem_desc(sa + (t * 2 + 0) * kTileBytes + j * 2 * kChunkBytes, kChunkBytes, 128);
-                            const uint64_t alo = smem_desc(sa + (t * 2 + 1) * kTileBytes + j * 2 * kChunkBytes, kChunkBytes, 128);
-                            mma_tf32_ss(dcol, ahi, bd, idesc_cat, (s | j) != 0);
-                            mma_tf32_ss(dcol, alo, bd, idesc_one, 1u);
+                            const uint64_t ahi = TMA ? smem_desc_sw64(sa + (t * 2 + 0) * kTileBytes + j * 32)
+                                                     : smem_desc(sa + (t * 2 + 0) * kTileBytes + j * 2 * kChunkBytes, kChunkBytes, 128);
+                            const uint64_t alo = TMA ? smem_desc_sw64(sa + (t * 2 + 1) * kTileBytes + j * 32)
+                                                     : smem_desc(sa + (t * 2 + 1) * kTileBytes + j * 2 * kChunkBytes, kChunkBytes, 128);
+                            if (!(UMMA_DBG & 1)) {
+                                mma_tf32_ss(dcol, ahi, bd, idesc_cat, (s | j) != 0);
+                                mma_tf32_ss(dcol, alo, bd, idesc_one, 1u);
+                            }
                         }
                     }
                     mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot
@@ -264,129 +290,208 @@ conv_umma_kernel(const ConvUArgs a) {
                 mma_commit(tfull_bar(buf));                            // ... and once the accumulators are final
             }
         }
-    } else {
-        // ------------------------------------------------------------------------------------------ operand builders
-        const int bt = tid - kBuild0, bw = bt >> 5;
-        // what a thread loads per stage
-        //   layers 2 / 3: four 16-byte chunks: rows R_i = 64 i + 8 bw + (lane & 7) of the pass, chunk c = lane >> 3
-        //   first layer:  its own row R = bt (16 scalars per stage: k = 16 s + 4 c + e -> (band, dy, dx))
-        constexpr int NV = CIN == 5 ? 4 : 4;
-        float4 rb[3][NV];
-        long long lpass = blockIdx.x;                                  // pass whose stages are being loaded
-        int ls = 0;                                                    // next stage of lpass to load
-        const float* src[4];                                           // layers 2 / 3: pixel (2 oy - 1, 2 ox - 1) + chunk, per row
-        uint32_t edge = 0;                                             // bit 2 i: row i at oy == 0, bit 2 i + 1: ox == 0
-        const float* src1 = nullptr;                                   // first layer: band 0, pixel (2 oy - 1, 2 ox - 1)
-        auto set_pass = [&](long long pass) {
-            const long long n = pass / half_tiles;
-            const int tile0 = (int)(pass - n * half_tiles) * kTPP;
-            if constexpr (CIN == 5) {
-                const int P = tile0 * 128 + bt;
-                const int oy = P / a.Wo, ox = P - oy * a.Wo;
-                src1 = a.in + (long long)n * 5 * a.H * a.W + (long long)(2 * oy - 1) * a.W + (2 * ox - 1);
-                edge = (oy == 0 ? 1u : 0u) | (ox == 0 ? 2u : 0u);
-            } else {
-                edge = 0;
+    } else if (warp == kTmaWarp) {
+        // ------------------------------------------------------------------------------------------ TMA producer (layers 2 / 3)
+        if constexpr (TMA) {
+            if (lane == 0) {
+                const int rows_per_tile = 128 / a.Wo;                  // output rows of one M tile
+                uint32_t it = 0;
+                for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x) {
+                    const long long n = pass / half_tiles;
+                    const int tile0 = (int)(pass - n * half_tiles) * kTPP;
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s, ++it) {
+                        const int slot = (int)(it % kSlots);
+                        const uint32_t sa = base + slot * Sh::SLOT;
+                        const int tap = s / G, g = s - tap * G;
+                        const int dy = tap / 3, dx = tap - 3 * dy;
+                        mbar_wait(empty_bar(slot), ((it / kSlots) & 1u) ^ 1u);
+                        mbar_arrive_expect_tx(full_bar(slot), kTPP * kTileBytes + ((UMMA_DBG & 4) ? 0u : Sh::B_BYTES));
+                        // the raw fp32 activations ARE the hi operand (the tensor core reads the upper 19 bits): box = 16 channels
+                        // x Wo pixels at stride 2 x (128 / Wo) rows at stride 2, zero-filled outside the image = the padding
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int P = tile0 * 128 + 64 * i + 8 * bw + (lane & 7);
-                    const int oy = P / a.Wo, ox = P - oy * a.Wo;
-                    src[i] = a.in + (((long long)n * a.H + (2 * oy - 1)) * a.W + (2 * ox - 1)) * CIN + 4 * (lane >> 3);
-                    edge |= (oy == 0 ? 1u : 0u) << (2 * i) | (ox == 0 ? 2u : 0u) << (2 * i);
+                        for (int t = 0; t < kTPP; ++t)
+                            tma_load_4d(sa + 2 * t * kTileBytes, &tmap, 16 * g, dx - 1, 2 * (tile0 + t) * rows_per_tile + dy - 1, (int)n,
+                                        full_bar(slot));
+                        if (!(UMMA_DBG & 4))
+                            bulk_g2s(sa + Sh::A_BYTES, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
+                    }
                 }
             }
-        };
-        auto load_stage = [&](int s, float4 (&dst)[NV]) {
-            if constexpr (CIN == 5) {
-                float v[16];
+        }
+    } else if constexpr (TMA) {
+        // ------------------------------------------------------------------------------------------ lo builders (layers 2 / 3)
+        // hi = x with the low 13 mantissa bits cleared is what the MMA makes of the raw tile; lo = x - hi is exact in fp32
+        // and is rounded to TF32 here (ties away, two integer instructions).  The lo tile mirrors the hi tile byte for byte,
+        // so the 64-byte swizzle never has to be spelled out.
+        const int bt = tid - kBuild0;
+        const long long my_passes = (a.passes - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const long long total = my_passes * S;
+        uint32_t it = 0;
+        for (long long q = 0; q < total; ++q, ++it) {
+            const int slot = (int)(it % kSlots);
+            const uint32_t sa = base + slot * Sh::SLOT;
+            mbar_wait(full_bar(slot), (it / kSlots) & 1u);
+            if (!(UMMA_DBG & 2)) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const int k = 16 * s + e;                          // compile-time after unrolling (s is u-derived)
-                    const int ch = k / 9, dy = (k % 9) / 3, dx = k % 3;
-                    const bool ok = k < 45 && !((dy == 0) && (edge & 1u)) && !((dx == 0) && (edge & 2u));
-                    v[e] = ok ? __ldg(src1 + ((long long)ch * a.H + dy) * a.W + dx) : 0.0f;
+                for (int i = 0; i < (int)(kTPP * kTileBytes / 16 / kBuildThreads); ++i) {
+                    const uint32_t chunk = (uint32_t)bt + (uint32_t)i * kBuildThreads;
+                    const uint32_t addr = sa + (chunk >> 9) * 2 * kTileBytes + (chunk & 511u) * 16u;
+                    uint32_t x0, x1, x2, x3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+                    auto lo = [](uint32_t x) {
+                        const float l = __uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u);
+                        return (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
+                    };
+                    st_shared_v4(addr + kTileBytes, lo(x0), lo(x1), lo(x2), lo(x3));
                 }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
+            mbar_arrive(lofull_bar(slot));
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------ operand builders
+        // Four groups of two warps; group g owns ring slot g and builds every fourth stage of the CTA's flat stage sequence.
+        // A group's loads are issued right after it has published a stage and are consumed one group-iteration later, so
+        // the proxy fence of a stage (a MEMBAR: it waits for every load the thread has in flight) never sees a prefetch;
+        // the global-load latency is hidden by the other three groups instead.
+        //   layers 2 / 3: 16 chunks of 16 bytes per thread and stage: rows R_i = 8 (2 i + w2) + (lane & 7), chunk c = lane >> 3
+        //   first layer:  4 rows R_i = 64 i + t64, 16 scalars each (k = 16 s + e -> (band, dy, dx), compile-time per stage)
+        const int bt = tid - kBuild0, grp = bt >> 6, t64 = bt & 63, w2 = (bt >> 5) & 1;
+        constexpr int NR = CIN == 5 ? 4 : 16;                          // rows per thread
+        const uint32_t sa = base + grp * Sh::SLOT;
+        const long long my_passes = (a.passes - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
+        float4 rb[16];
+        int offs[NR];                                                  // element offset of input pixel (2 oy - 1, 2 ox - 1) in the patch
+        uint32_t edge = 0;                                             // bit 2 i: row i at oy == 0, bit 2 i + 1: ox == 0
+        const float* pbase = a.in;
+        long long cur = -1;
+        auto set_pass = [&](long long pl) {
+            cur = pl;
+            const long long pass = (long long)blockIdx.x + pl * gridDim.x;
+            const long long n = pass / half_tiles;
+            const int tile0 = (int)(pass - n * half_tiles) * kTPP;
+            pbase = a.in + (long long)n * CIN * a.H * a.W;
+            edge = 0;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            for (int i = 0; i < NR; ++i) {
+                const int R = CIN == 5 ? 64 * i + t64 : 8 * (2 * i + w2) + (lane & 7);
+                const int P = tile0 * 128 + R;
+                const int oy = P / a.Wo, ox = P - oy * a.Wo;
+                offs[i] = CIN == 5 ? (2 * oy - 1) * a.W + (2 * ox - 1) : ((2 * oy - 1) * a.W + (2 * ox - 1)) * CIN + 4 * (lane >> 3);
+                edge |= ((oy == 0 ? 1u : 0u) | (ox == 0 ? 2u : 0u)) << (2 * i);
+            }
+        };
+        auto load_stage = [&](int s) {
+            if constexpr (CIN == 5) {
+#pragma unroll
+                for (int sc = 0; sc < 3; ++sc)
+                    if (s == sc) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float v[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const int k = 16 * sc + e;
+                                const int ch = k / 9, dy = (k % 9) / 3, dx = k % 3;
+                                const bool ok = k < 45 && !((dy == 0) && ((edge >> (2 * i)) & 1u)) && !((dx == 0) && ((edge >> (2 * i + 1)) & 1u));
+                                v[e] = ok ? __ldg(pbase + ((long long)ch * a.H + dy) * a.W + dx + offs[i]) : 0.0f;
+                            }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) rb[4 * i + c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        }
+                    }
             } else {
                 const int tap = s / G, g = s - tap * G;
                 const int dy = tap / 3, dx = tap - 3 * dy;
-                const long long off = ((long long)dy * a.W + dx) * CIN + 16 * g;
+                const float* p = pbase + ((long long)dy * a.W + dx) * CIN + 16 * g;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     const bool ok = !((dy == 0) && ((edge >> (2 * i)) & 1u)) && !((dx == 0) && ((edge >> (2 * i + 1)) & 1u));
-                    dst[i] = ok ? __ldg(reinterpret_cast<const float4*>(src[i] + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rb[i] = ok ? __ldg(reinterpret_cast<const float4*>(p + offs[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         };
-        // where they go inside a slot: tile t, part p (hi / lo), chunk c, row r -> (2 t + p) 8192 + 2048 c + 128 (r / 8) + 16 (r % 8)
-        uint32_t dsto[4];
-        if constexpr (CIN == 5) {
-            const int t = bt >> 7, r = bt & 127;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dsto[c] = (2 * t) * kTileBytes + c * kChunkBytes + (r >> 3) * 128 + (r & 7) * 16;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                dsto[i] = (2 * (i >> 1)) * kTileBytes + (lane >> 3) * kChunkBytes + ((i & 1) * 8 + bw) * 128 + (lane & 7) * 16;
-        }
-        auto store_stage = [&](uint32_t slot_base, const float4 (&v)[NV]) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t h0 = tf32_rna(v[i].x), h1 = tf32_rna(v[i].y), h2 = tf32_rna(v[i].z), h3 = tf32_rna(v[i].w);
-                st_shared_v4(slot_base + dsto[i], h0, h1, h2, h3);
-                st_shared_v4(slot_base + dsto[i] + kTileBytes, tf32_rna(v[i].x - __uint_as_float(h0)),
-                             tf32_rna(v[i].y - __uint_as_float(h1)), tf32_rna(v[i].z - __uint_as_float(h2)),
-                             tf32_rna(v[i].w - __uint_as_float(h3)));
+        // where a chunk goes inside the slot: tile t, part (hi / lo), chunk c, row r -> (2 t + part) 8192 + 2048 c + 128 (r / 8) + 16 (r % 8)
+        auto chunk_dst = [&](int j) -> uint32_t {
+            if constexpr (CIN == 5) {
+                const int R = 64 * (j >> 2) + t64, c = j & 3;
+                return (uint32_t)((2 * (R >> 7)) * kTileBytes + c * kChunkBytes + ((R & 127) >> 3) * 128 + (R & 7) * 16);
+            } else {
+                const int rg = 2 * j + w2;                             // row group of 8 among the pass's 32
+                return (uint32_t)((2 * (rg >> 4)) * kTileBytes + (lane >> 3) * kChunkBytes + (rg & 15) * 128 + (lane & 7) * 16);
             }
         };
-
-        if (lpass < a.passes) {
-            set_pass(lpass);
-            load_stage(0, rb[0]);
-            load_stage(1, rb[1]);
-        }
-        ls = 2;
-        uint32_t it = 0;
-        for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x) {
-#pragma unroll 1
-            for (int s0 = 0; s0 < S; s0 += 3) {
+        // TF32 split: the hi tile holds x itself (the tensor core reads its upper 19 bits, i.e. truncates); lo = x minus the
+        // truncated x is exact in fp32 and is rounded to TF32 (ties away, two integer instructions)
+        auto store_stage = [&]() {
 #pragma unroll
-                for (int u = 0; u < 3; ++u, ++it) {
-                    // loads of the stage two ahead (possibly of the next pass)
-                    if (ls == S) {
-                        ls = 0;
-                        lpass += gridDim.x;
-                        if (lpass < a.passes) set_pass(lpass);
-                    }
-                    if (lpass < a.passes) load_stage(CIN == 5 ? (u + 2) % 3 : ls, rb[(u + 2) % 3]);
-                    ++ls;
-                    const int slot = (int)(it % kSlots);
-                    const uint32_t sa = base + slot * Sh::SLOT;
-                    mbar_wait(empty_bar(slot), ((it / kSlots) & 1u) ^ 1u);
-                    if (bt == 0) {
-                        mbar_arrive_expect_tx(full_bar(slot), Sh::B_BYTES);
-                        bulk_g2s(sa + Sh::A_BYTES, a.wst + (size_t)(s0 + u) * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
-                    }
-                    store_stage(sa, rb[u]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
-                    mbar_arrive(full_bar(slot));
+            for (int j = 0; j < 16; ++j) {
+                const float4 v = rb[j];
+                const uint32_t d = sa + chunk_dst(j);
+                auto lo = [](float x) {
+                    const float l = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                    return (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
+                };
+                st_shared_v4(d, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                st_shared_v4(d + kTileBytes, lo(v.x), lo(v.y), lo(v.z), lo(v.w));
+            }
+        };
+        // flat stage sequence of this CTA: (local pass pl, stage s), this group takes every fourth
+        long long pl = 0;
+        int s = grp;
+        while (s >= S) { s -= S; ++pl; }
+        if (pl < my_passes && !(UMMA_DBG & 2)) {
+            set_pass(pl);
+            load_stage(s);
+        }
+        for (uint32_t m = 0; pl < my_passes; ++m) {
+            mbar_wait(empty_bar(grp), (m & 1u) ^ 1u);
+            if (t64 == 0) {
+                if (UMMA_DBG & 4) mbar_arrive(full_bar(grp));
+                else {
+                    mbar_arrive_expect_tx(full_bar(grp), Sh::B_BYTES);
+                    bulk_g2s(sa + Sh::A_BYTES, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(grp));
                 }
+            }
+            if (!(UMMA_DBG & 2)) store_stage();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
+            mbar_arrive(full_bar(grp));
+            s += kSlots;
+            while (s >= S) { s -= S; ++pl; }
+            if (pl < my_passes && !(UMMA_DBG & 2)) {
+                if (pl != cur) set_pass(pl);
+                load_stage(s);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kEpiWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
+    if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
 }
 
 template <int CIN, int COUT, bool POOL>
-int launch_conv_umma(const ConvUArgs& a, int sms, cudaStream_t st) {
+int launch_conv_umma(const ConvUArgs& a, long long N, int sms, cudaStream_t st) {
     using Sh = Shape<CIN, COUT>;
     auto kern = conv_umma_kernel<CIN, COUT, POOL>;
     KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::SMEM));
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (CIN != 5) {
+        // channel-last activations [N, H, W, CIN] seen as (c, x, y, n); one box = one 128-pixel M tile of one 16-channel
+        // group of one tap: 16 channels x Wo pixels (every second column) x 128 / Wo rows (every second row), 64-byte swizzle
+        EncodeTiledFn enc = get_tensor_map_encoder();
+        KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled is not available");
+        cuuint64_t gdim[4] = {(cuuint64_t)CIN, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)N};
+        cuuint64_t gstr[3] = {(cuuint64_t)CIN * 4, (cuuint64_t)a.W * CIN * 4, (cuuint64_t)a.H * a.W * CIN * 4};
+        cuuint32_t box[4] = {16, (cuuint32_t)(2 * a.Wo), (cuuint32_t)(2 * (128 / a.Wo)), 1};
+        cuuint32_t estr[4] = {1, 2, 2, 1};
+        CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+    }
     const unsigned grid = (unsigned)(a.passes < sms ? a.passes : sms);
-    kern<<<grid, kThreads, Sh::SMEM, st>>>(a);
+    kern<<<grid, kThreads, Sh::SMEM, st>>>(tmap, a);
     KMSR_LAUNCH_CHECK("conv_umma_kernel");
     return KMSR_OK;
 }
