@@ -275,6 +275,22 @@ KMSR_API int kmsr_selector_logits(const float* x, int64_t N, int H, int W,
                                   const float* w3, const float* b3, const float* fc_w, const float* fc_b,
                                   float* logits, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same logits through the 5th-generation tensor cores (csrc/selector_umma.cuh: tcgen05.mma kind::tf32, accumulators
+ * in tensor memory, the activations of layers 2 / 3 fetched as strided TMA boxes, 3xTF32 split as two MMAs per k-step).
+ * Shapes: kmsr_selector_umma_supported(H, W) != 0 (H, W multiples of 8, W in {64, 128, 256}, an even number of 128-pixel
+ * tiles per layer; 256 x 256 and 128 x 128 patches qualify).  Weight blobs are the per-stage shared-memory images
+ * [stage][4][2 cout / 8][8][4] (rows < cout: TF32 hi part, rows >= cout: lo part; kmsr_b200/selector.py builds them),
+ * kmsr_selector_umma_weight_floats(cin, cout) floats each, 16-byte aligned; x 16-byte aligned; biases / fc as above.
+ * workspace: kmsr_selector_umma_workspace_bytes(N, H, W), 256-byte aligned.  Replaces the same reference forward as
+ * kmsr_selector_logits (train_gemini.py:35-39); other shapes return KMSR_E_UNSUPPORTED. */
+KMSR_API int kmsr_selector_umma_supported(int H, int W);
+KMSR_API int64_t kmsr_selector_umma_weight_floats(int cin, int cout);
+KMSR_API int64_t kmsr_selector_umma_workspace_bytes(int64_t N, int H, int W);
+KMSR_API int kmsr_selector_logits_umma(const float* x, int64_t N, int H, int W,
+                                       const float* w1, const float* b1, const float* w2, const float* b2,
+                                       const float* w3, const float* b3, const float* fc_w, const float* fc_b,
+                                       float* logits, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------
  * Launch counter: number of kernels this library launched on the calling process since load.   */
 KMSR_API int64_t kmsr_launch_count(void);

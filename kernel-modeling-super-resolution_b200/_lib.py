@@ -72,6 +72,10 @@ SIGNATURES = {
     "kmsr_selector_weight_floats": (_i64, [_i32, _i32]),
     "kmsr_selector_workspace_bytes": (_i64, [_i64, _i32, _i32]),
     "kmsr_selector_logits": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "kmsr_selector_umma_supported": (_i32, [_i32, _i32]),
+    "kmsr_selector_umma_weight_floats": (_i64, [_i32, _i32]),
+    "kmsr_selector_umma_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "kmsr_selector_logits_umma": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "kmsr_launch_count": (_i64, []),
     "kmsr_last_algo": (C.c_char_p, []),
 }

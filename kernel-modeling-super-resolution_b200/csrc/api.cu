@@ -41,6 +41,11 @@ int launch_nlm(const float*, long long, int, int, int, long long, const double*,
 bool nlm_shape_ok(int, int, const char**);
 int launch_fp32_probe(float*, int, double*, cudaStream_t);
 int launch_validate_indices(const int*, long long, long long, int*, int*, cudaStream_t);
+bool selector_umma_shape_ok(int, int);
+long long selector_umma_wfloats(int, int);
+long long selector_umma_workspace(long long, int, int);
+int launch_selector_umma(const float*, long long, int, int, const float*, const float*, const float*, const float*, const float*,
+                         const float*, const float*, const float*, float*, void*, long long, cudaStream_t);
 long long selector_wsplit_floats(int, int);
 long long selector_workspace(long long, int, int);
 int launch_selector(const float*, long long, int, int, const float*, const float*, const float*, const float*, const float*,
@@ -418,6 +423,35 @@ KMSR_API int kmsr_selector_logits(const float* x, int64_t N, int H, int W, const
                  "selector_logits: null pointer");
     return launch_selector(x, N, H, W, w1, b1, w2, b2, w3, b3, fc_w, fc_b, logits, workspace, workspace_bytes,
                            (cudaStream_t)stream);
+}
+
+KMSR_API int kmsr_selector_umma_supported(int H, int W) { return selector_umma_shape_ok(H, W) ? 1 : 0; }
+
+KMSR_API int64_t kmsr_selector_umma_weight_floats(int cin, int cout) {
+    if (!((cin == 5 || (cin >= 16 && cin % 16 == 0)) && cout >= 16 && cout <= 128 && cout % 16 == 0)) {
+        set_error("selector_umma_weight_floats: cin=%d cout=%d", cin, cout);
+        return KMSR_E_INVALID;
+    }
+    return selector_umma_wfloats(cin, cout);
+}
+
+KMSR_API int64_t kmsr_selector_umma_workspace_bytes(int64_t N, int H, int W) {
+    if (N < 0 || !selector_umma_shape_ok(H, W)) {
+        set_error("selector_umma_workspace_bytes: N=%lld H=%d W=%d", (long long)N, H, W);
+        return KMSR_E_INVALID;
+    }
+    return selector_umma_workspace(N, H, W);
+}
+
+KMSR_API int kmsr_selector_logits_umma(const float* x, int64_t N, int H, int W, const float* w1, const float* b1, const float* w2,
+                                       const float* b2, const float* w3, const float* b3, const float* fc_w, const float* fc_b,
+                                       float* logits, void* workspace, int64_t workspace_bytes, void* stream) {
+    KMSR_REQUIRE(N >= 0 && H >= 1 && W >= 1, KMSR_E_INVALID, "selector_logits_umma: N=%lld H=%d W=%d", (long long)N, H, W);
+    if (N == 0) return KMSR_OK;
+    KMSR_REQUIRE(x && w1 && b1 && w2 && b2 && w3 && b3 && fc_w && fc_b && logits && workspace, KMSR_E_INVALID,
+                 "selector_logits_umma: null pointer");
+    return launch_selector_umma(x, N, H, W, w1, b1, w2, b2, w3, b3, fc_w, fc_b, logits, workspace, workspace_bytes,
+                                (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -248,6 +248,14 @@ inline int conv_out(int h) { return (h - 1) / 2 + 1; }       // (h + 2 - 3) / 2 
 
 }  // namespace
 
+// pooling + linear layer for the tcgen05 path (selector_umma.cu), which produces the same per-tile channel sums
+int launch_pool_fc(const float* part, int tiles, int C, float inv_area, const float* fc_w, const float* fc_b, int classes, long long N,
+                   float* logits, cudaStream_t st) {
+    pool_fc_kernel<<<(unsigned)((N + 3) / 4), 128, 0, st>>>(part, tiles, C, inv_area, fc_w, fc_b, classes, N, logits);
+    KMSR_LAUNCH_CHECK("pool_fc_kernel");
+    return KMSR_OK;
+}
+
 // floats of the split weight blob of one layer: chunks x nblk x 9 taps x NT quads x 32 lanes x 4
 long long selector_wsplit_floats(int cin, int cout) {
     const int NT = cout >= 64 ? 8 : 4;

@@ -37,7 +37,10 @@ constexpr int kBuildThreads = 32 * kBuildWarps;
 constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1;
 constexpr int kBuild0 = 32 * (kEpiWarps + 2);                  // first builder thread
 constexpr int kThreads = kBuild0 + kBuildThreads;              // 448
-constexpr int kSlots = 4;                                      // operand ring
+#ifndef UMMA_SLOTS
+#define UMMA_SLOTS 4
+#endif
+constexpr int kSlots = UMMA_SLOTS;                             // operand ring
 constexpr int kTPP = 2;                                        // M tiles per pass
 constexpr uint32_t kTileBytes = 8192;                          // one 128 x 16 fp32 operand tile: [4 chunks][16 groups][8 rows][16 B]
 constexpr uint32_t kChunkBytes = 2048;                         // LBO of the A tiles (core matrices adjacent in K)
@@ -293,7 +296,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const ConvUArgs a) {
     } else if (warp == kTmaWarp) {
         // ------------------------------------------------------------------------------------------ TMA producer (layers 2 / 3)
         if constexpr (TMA) {
-            if (lane == 0) {
+            // three lanes, one request each per stage (a single thread sustains about one TMA request per 280 ns):
+            // lanes 0 / 1 the two M tiles' boxes, lane 2 the weight stage; lane 0 also posts the byte count
+            if (lane < kTPP + 1) {
                 const int rows_per_tile = 128 / a.Wo;                  // output rows of one M tile
                 uint32_t it = 0;
                 for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x) {
@@ -306,14 +311,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const ConvUArgs a) {
                         const int tap = s / G, g = s - tap * G;
                         const int dy = tap / 3, dx = tap - 3 * dy;
                         mbar_wait(empty_bar(slot), ((it / kSlots) & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(full_bar(slot), kTPP * kTileBytes + ((UMMA_DBG & 4) ? 0u : Sh::B_BYTES));
+                        if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), kTPP * kTileBytes + ((UMMA_DBG & 4) ? 0u : Sh::B_BYTES));
                         // the raw fp32 activations ARE the hi operand (the tensor core reads the upper 19 bits): box = 16 channels
                         // x Wo pixels at stride 2 x (128 / Wo) rows at stride 2, zero-filled outside the image = the padding
-#pragma unroll
-                        for (int t = 0; t < kTPP; ++t)
-                            tma_load_4d(sa + 2 * t * kTileBytes, &tmap, 16 * g, dx - 1, 2 * (tile0 + t) * rows_per_tile + dy - 1, (int)n,
+                        if (lane < kTPP)
+                            tma_load_4d(sa + 2 * lane * kTileBytes, &tmap, 16 * g, dx - 1, 2 * (tile0 + lane) * rows_per_tile + dy - 1, (int)n,
                                         full_bar(slot));
-                        if (!(UMMA_DBG & 4))
+                        else if (!(UMMA_DBG & 4))
                             bulk_g2s(sa + Sh::A_BYTES, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
                     }
                 }

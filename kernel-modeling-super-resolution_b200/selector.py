@@ -43,6 +43,8 @@ class Selector:
         self.fc_b = t["classifier.bias"].float()
         self.device = dev
         self._cuda = None
+        self._umma = None
+        self.last_algo = None
 
     @classmethod
     def from_state_dict_file(cls, path: str, device=None) -> "Selector":
@@ -60,6 +62,7 @@ class Selector:
         self.layers = [tuple(p.to(dev) for p in layer) for layer in self.layers]
         self.fc_w, self.fc_b, self.device = self.fc_w.to(dev), self.fc_b.to(dev), dev
         self._cuda = None
+        self._umma = None
         return self
 
     # ---- libkmsr path ---------------------------------------------------------------------------------------------
@@ -104,31 +107,85 @@ class Selector:
             blobs.append((torch.from_numpy(blob.reshape(-1)).to(dev), torch.from_numpy(bf).to(dev)))
         self._cuda = (dev, blobs, self.fc_w.to(dev).contiguous(), self.fc_b.to(dev).contiguous())
 
+    def _folded(self):
+        """(weight [cout, cin, 3, 3] float32, bias [cout] float32) per layer with eval-mode BatchNorm folded in (fp64)."""
+        out = []
+        for w, b, g, beta, mean, var in self.layers:
+            w64, b64 = w.double().cpu().numpy(), b.double().cpu().numpy()
+            sc = g.double().cpu().numpy() / np.sqrt(var.double().cpu().numpy() + _BN_EPS)
+            out.append(((w64 * sc[:, None, None, None]).astype(np.float32),
+                        ((b64 - mean.double().cpu().numpy()) * sc + beta.double().cpu().numpy()).astype(np.float32)))
+        return out
+
+    @classmethod
+    def umma_stage_images(cls, wf: np.ndarray) -> np.ndarray:
+        """Weight stages of conv_umma_kernel (csrc/selector_umma.cuh) for a folded weight [cout, cin, 3, 3]:
+        float32 [stage][4 chunks][2 cout / 8][8][4] -- per stage of 16 values of K the shared-memory image of the operand
+        [B_hi ; B_lo] in the K-major canonical layout without swizzle (core matrix = 8 rows x 16 bytes).  Rows < cout hold the
+        TF32 hi part of output channel `row`, rows >= cout the lo part of channel `row - cout`.  K runs tap-major in groups
+        of 16 input channels (stage = tap * cin / 16 + group, k = 16 group + 4 chunk + e); the 5-channel first layer uses
+        k = 16 stage + 4 chunk + e = 9 band + tap, zero from 45 to 47."""
+        cout, cin = wf.shape[0], wf.shape[1]
+        w9 = wf.reshape(cout, cin, 9)
+        if cin == 5:
+            stages = 3
+            flat = np.zeros((cout, 48), dtype=np.float32)
+            flat[:, :45] = w9.reshape(cout, 45)                                   # k = 9 band + tap
+        else:
+            assert cin % 16 == 0, cin
+            stages = 9 * (cin // 16)
+            flat = np.ascontiguousarray(w9.transpose(0, 2, 1)).reshape(cout, 9 * cin)   # k = tap * cin + channel
+        hi = cls._tf32(flat)
+        lo = cls._tf32(flat - hi)
+        cat = np.concatenate([hi, lo], axis=0)                                    # [2 cout, K]
+        img = cat.reshape(2 * cout // 8, 8, stages, 4, 4).transpose(2, 3, 0, 1, 4)  # [stage][chunk][row group][row][e]
+        return np.ascontiguousarray(img, dtype=np.float32)
+
+    def _prepare_umma(self, dev):
+        blobs = []
+        for wf, bf in self._folded():
+            img = self.umma_stage_images(wf)
+            assert img.size == L.check(int(L.lib().kmsr_selector_umma_weight_floats(wf.shape[1], wf.shape[0])))
+            blobs.append((torch.from_numpy(img.reshape(-1)).to(dev), torch.from_numpy(bf).to(dev)))
+        self._umma = (dev, blobs, self.fc_w.to(dev).contiguous(), self.fc_b.to(dev).contiguous())
+
     @torch.no_grad()
-    def logits(self, x: torch.Tensor, batch: int = 4096) -> torch.Tensor:
+    def logits(self, x: torch.Tensor, batch: int = 4096, algo: str = "auto") -> torch.Tensor:
         """x [N,5,H,W] float32 -> logits [N,10].  CUDA tensors go through libkmsr (3xTF32 tensor-core convolutions with
-        folded BatchNorm); CPU tensors through the torch fp32 evaluation."""
+        folded BatchNorm); CPU tensors through the torch fp32 evaluation.  `algo`: "umma" = the tcgen05 / tensor-memory
+        kernels (256 x 256, 128 x 128, ... patches: kmsr_selector_umma_supported), "mma" = the mma.sync kernels (any
+        shape), "auto" = umma where the shape qualifies."""
         if not x.is_cuda:
             return self.logits_library(x)
         ops.require_cuda()
         dev = x.device
-        if getattr(self, "_cuda", None) is None or self._cuda[0] != dev:
-            self._prepare(dev)
-        _, blobs, fc_w, fc_b = self._cuda
         x = x.to(torch.float32).contiguous()
         n, c, h, w = x.shape
         assert c == 5, f"SelectorNet takes 5 bands, got {c}"
+        if algo not in ("auto", "umma", "mma"):
+            raise ValueError(f"algo must be 'auto', 'umma' or 'mma', got {algo!r}")
+        umma = algo == "umma" or (algo == "auto" and bool(L.lib().kmsr_selector_umma_supported(h, w)))
+        if umma:
+            if getattr(self, "_umma", None) is None or self._umma[0] != dev:
+                self._prepare_umma(dev)
+            _, blobs, fc_w, fc_b = self._umma
+            ws_fn, fn = L.lib().kmsr_selector_umma_workspace_bytes, L.lib().kmsr_selector_logits_umma
+        else:
+            if getattr(self, "_cuda", None) is None or self._cuda[0] != dev:
+                self._prepare(dev)
+            _, blobs, fc_w, fc_b = self._cuda
+            ws_fn, fn = L.lib().kmsr_selector_workspace_bytes, L.lib().kmsr_selector_logits
+        self.last_algo = "umma" if umma else "mma"
         out = torch.empty((n, 10), dtype=torch.float32, device=dev)
         p = lambda t: C.c_void_p(t.data_ptr())
         with torch.cuda.device(dev):
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             for a in range(0, n, batch):
                 m = min(batch, n - a)
-                wsb = L.check(int(L.lib().kmsr_selector_workspace_bytes(m, h, w)))
+                wsb = L.check(int(ws_fn(m, h, w)))
                 ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-                L.check(L.lib().kmsr_selector_logits(p(x[a:a + m]), m, h, w, p(blobs[0][0]), p(blobs[0][1]), p(blobs[1][0]),
-                                                     p(blobs[1][1]), p(blobs[2][0]), p(blobs[2][1]), p(fc_w), p(fc_b),
-                                                     p(out[a:a + m]), p(ws), wsb, st))
+                L.check(fn(p(x[a:a + m]), m, h, w, p(blobs[0][0]), p(blobs[0][1]), p(blobs[1][0]), p(blobs[1][1]),
+                           p(blobs[2][0]), p(blobs[2][1]), p(fc_w), p(fc_b), p(out[a:a + m]), p(ws), wsb, st))
         return out
 
     @torch.no_grad()

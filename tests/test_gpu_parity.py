@@ -852,6 +852,52 @@ def test_selector_kernels_match_the_fp32_library_forward(K, golden, synth):
     assert sel.logits(torch.zeros((0, 5, 64, 64), device="cuda")).shape == (0, 10)
 
 
+def test_selector_tcgen05_path(K, golden, synth):
+    """kmsr_selector_logits_umma (csrc/selector_umma.cuh: tcgen05.mma kind::tf32 with TMEM accumulators, strided TMA boxes as
+    the hi operand, the lo operand built in shared memory) against the torch fp32 forward (TF32 disabled), against the
+    mma.sync kernels and against the golden logits of the reference module (train_gemini.py:35-39): logits to 5e-5 of
+    their scale, identical argmax, bit-identical run to run; shapes the path refuses fall back (auto) or raise (umma)."""
+    from kmsr_b200.selector import Selector
+    z = golden("selector.npz")
+    sel = Selector.from_npz(z, "cuda")
+    worst = 0.0
+    for n, h, w in ((6, 256, 256), (301, 256, 256), (5, 128, 128), (3, 64, 256), (4, 256, 128), (2, 512, 256), (3, 256, 64)):
+        assert K.lib.lib().kmsr_selector_umma_supported(h, w) == 1, (h, w)
+        rs = np.random.RandomState(h + w)
+        x = torch.from_numpy((rs.standard_normal((n, 5, h, w)) * 3.0 + np.array([80, 70, 50, 25, 8])[None, :, None, None])
+                             .astype(np.float32)).cuda()
+        a = sel.logits(x)
+        assert sel.last_algo == "umma"
+        b = sel.logits_library(x)
+        c = sel.logits(x, algo="mma")
+        assert sel.last_algo == "mma"
+        scale = float(b.abs().max())
+        worst = max(worst, float((a - b).abs().max()) / scale)
+        assert float((a - b).abs().max()) <= 5e-5 * scale, (n, h, w, float((a - b).abs().max()) / scale)
+        assert float((a - c).abs().max()) <= 5e-5 * scale
+        assert torch.equal(a.argmax(1), b.argmax(1))
+        assert torch.equal(a, sel.logits(x, algo="umma"))
+    print(f"tcgen05 selector vs fp32 library forward: worst {worst:.2e} of the logit scale")
+    hr = np.concatenate([synth.make_hr(4, 5100, "textured"), synth.make_hr(2, 5101, "water")])
+    lg = sel.logits(torch.from_numpy(hr).cuda(), algo="umma").cpu().numpy()
+    assert np.abs(lg - z["logits"][:6]).max() <= 1e-4 * np.abs(z["logits"]).max()
+    assert np.array_equal(lg.argmax(1), z["argmax"][:6])
+    # NaN patches give NaN logits, as the reference forward does, and do not disturb their neighbours
+    xn = torch.from_numpy(hr).cuda()
+    xn[1, 2, 100, 37] = float("nan")
+    ln = sel.logits(xn, algo="umma").cpu().numpy()
+    assert np.isnan(ln[1]).all() and np.array_equal(ln[[0, 2, 3, 4, 5]], lg[[0, 2, 3, 4, 5]])
+    # shapes outside the path
+    for h, w in ((100, 100), (17, 33), (128, 64), (256, 512)):
+        assert K.lib.lib().kmsr_selector_umma_supported(h, w) == 0
+        x = torch.randn((2, 5, h, w), device="cuda")
+        sel.logits(x)
+        assert sel.last_algo == "mma"
+        with pytest.raises(K.lib.KmsrError):
+            sel.logits(x, algo="umma")
+    assert sel.logits(torch.zeros((0, 5, 256, 256), device="cuda"), algo="umma").shape == (0, 10)
+
+
 @pytest.mark.parametrize("h,w,k,s,algo", [(64, 256, 13, 8, "tma"), (8, 256, 13, 8, "tma"), (16, 256, 13, 8, "tma"), (248, 256, 13, 8, "tma"),
                                           (64, 512, 13, 8, "tma"),
                                           (96, 128, 11, 4, "stream"), (8, 64, 15, 8, "stream"), (40, 512, 21, 2, "stream"),

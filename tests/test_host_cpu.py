@@ -342,6 +342,41 @@ def test_selector_weight_blobs_reproduce_the_reference_forward(golden):
     assert np.array_equal(lg.argmax(1), ref.argmax(1))
 
 
+def test_selector_tcgen05_weight_stages_reproduce_the_reference_forward(golden):
+    """Host side of the tcgen05 selector path (Selector.umma_stage_images, no GPU): the per-stage shared-memory images
+    [stage][4 chunks][2 cout / 8][8][4] are read back the way conv_umma_kernel's descriptors address them (K-major
+    canonical layout without swizzle: row n, value k of a stage at chunk k // 4, row group n // 8, row n % 8, element
+    k % 4; rows < cout = TF32 hi part, rows >= cout = lo part; stage = tap * cin / 16 + group, the first layer
+    k = 9 band + tap) and a float64 forward through hi + lo must give the logits of the torch fp32 forward."""
+    from kmsr_b200.selector import Selector
+    z = golden("selector.npz")
+    sel = Selector.from_npz(z, "cpu")
+
+    def dense(img, cin, cout):
+        stages = img.shape[0]
+        assert img.shape == (stages, 4, 2 * cout // 8, 8, 4)
+        assert np.all((img.view(np.uint32) & 0x1FFF) == 0)                       # every value is a TF32 number
+        rows = img.transpose(2, 3, 0, 1, 4).reshape(2 * cout, stages * 16).astype(np.float64)   # [row][k]
+        both = rows[:cout] + rows[cout:]
+        if cin == 5:
+            assert stages == 3 and np.abs(both[:, 45:]).max() == 0.0
+            return both[:, :45].reshape(cout, 5, 3, 3)
+        assert stages == 9 * (cin // 16)
+        return both.reshape(cout, 9, cin).transpose(0, 2, 1).reshape(cout, cin, 3, 3)
+
+    rs = np.random.RandomState(4)
+    x = (rs.standard_normal((2, 5, 40, 56)) * 3.0 + 50.0).astype(np.float32)
+    h = torch.from_numpy(x).double()
+    for (wf, bf), (cin, cout) in zip(sel._folded(), ((5, 32), (32, 64), (64, 128))):
+        w = dense(Selector.umma_stage_images(wf), cin, cout)
+        assert np.abs(w - wf).max() <= 2.0 ** -21 * np.abs(wf).max()
+        h = torch.relu(torch.nn.functional.conv2d(h, torch.from_numpy(w), torch.from_numpy(bf).double(), stride=2, padding=1))
+    lg = torch.nn.functional.linear(h.mean(dim=(2, 3)), sel.fc_w.double(), sel.fc_b.double()).numpy()
+    ref = sel.logits_library(torch.from_numpy(x)).numpy()
+    assert np.abs(lg - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.array_equal(lg.argmax(1), ref.argmax(1))
+
+
 def test_reference_arm_loader_prefers_the_verbatim_reference(monkeypatch, tmp_path):
     """oracle/refarm.py: the verbatim reference function when a copy is reachable (KMSR_REFERENCE_ROOT, baseline/_ref,
     /root/reference), else the call-site port -- and both give the same pairs on the same inputs."""
