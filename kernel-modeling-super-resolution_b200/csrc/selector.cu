@@ -31,6 +31,8 @@ constexpr int kIH = 2 * kTH + 1, kIW = 2 * kTW + 1;   // input pixels per CTA (s
 constexpr int kCS = 10;                          // floats per staged pixel (8 channels + 2: bank-conflict-free at stride 2)
 constexpr int kInF = (kIH * kIW * kCS + 3) / 4 * 4;   // floats per staged input chunk (the weights behind it take 16-byte copies)
 
+// ReLU as torch evaluates it: a NaN stays a NaN (fmaxf would return 0)
+__device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.0f ? 0.0f : v; }
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -170,7 +172,7 @@ conv_mma_kernel(const ConvArgs a) {
                     const int oy = oy0 + 4 * warp + 2 * m + (r >> 1), ox = ox0 + g;
                     const int co = cbase + 8 * j + 2 * t + (r & 1);
                     if (oy < a.Ho && ox < a.Wo)
-                        a.out[((n * a.COUT + co) * a.Ho + oy) * (long long)a.Wo + ox] = fmaxf(acc[m][j][r] + __ldg(a.bias + co), 0.0f);
+                        a.out[((n * a.COUT + co) * a.Ho + oy) * (long long)a.Wo + ox] = relu_keep_nan(acc[m][j][r] + __ldg(a.bias + co));
                 }
         return;
     }
@@ -188,7 +190,7 @@ conv_mma_kernel(const ConvArgs a) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int oy = oy0 + 4 * warp + 2 * m + h, ox = ox0 + g;
-                    if (oy < a.Ho && ox < a.Wo) s += fmaxf(acc[m][j][2 * h + q] + b, 0.0f);
+                    if (oy < a.Ho && ox < a.Wo) s += relu_keep_nan(acc[m][j][2 * h + q] + b);
                 }
             // over the 8 pixel columns g (lane bits 2..4)
             s += __shfl_xor_sync(0xffffffffu, s, 4);

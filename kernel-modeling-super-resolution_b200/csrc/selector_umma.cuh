@@ -56,6 +56,8 @@ struct ConvUArgs {
     long long passes;       // N tiles / 2
 };
 
+// ReLU as torch evaluates it: a NaN stays a NaN (fmaxf would return 0)
+__device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.0f ? 0.0f : v; }
 __device__ __forceinline__ uint32_t tf32_rna(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -209,10 +211,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const ConvUArgs a) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             float4 o;
-                            o.x = fmaxf(p[j] + q[j] + bias_s[j0 + j], 0.0f);
-                            o.y = fmaxf(p[j + 1] + q[j + 1] + bias_s[j0 + j + 1], 0.0f);
-                            o.z = fmaxf(p[j + 2] + q[j + 2] + bias_s[j0 + j + 2], 0.0f);
-                            o.w = fmaxf(p[j + 3] + q[j + 3] + bias_s[j0 + j + 3], 0.0f);
+                            o.x = relu_keep_nan(p[j] + q[j] + bias_s[j0 + j]);
+                            o.y = relu_keep_nan(p[j + 1] + q[j + 1] + bias_s[j0 + j + 1]);
+                            o.z = relu_keep_nan(p[j + 2] + q[j + 2] + bias_s[j0 + j + 2]);
+                            o.w = relu_keep_nan(p[j + 3] + q[j + 3] + bias_s[j0 + j + 3]);
                             *reinterpret_cast<float4*>(dst + j0 + j) = o;
                         }
                     }
@@ -226,12 +228,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const ConvUArgs a) {
                             tmem_ld16(q, tcol + COUT + j0);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = fmaxf(p[j] + q[j] + bias_s[j0 + j], 0.0f);
+                            for (int j = 0; j < 16; ++j) v[j] = relu_keep_nan(p[j] + q[j] + bias_s[j0 + j]);
                             tmem_ld16(p, tcol + j0 + 16);
                             tmem_ld16(q, tcol + COUT + j0 + 16);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[16 + j] = fmaxf(p[j] + q[j] + bias_s[j0 + 16 + j], 0.0f);
+                            for (int j = 0; j < 16; ++j) v[16 + j] = relu_keep_nan(p[j] + q[j] + bias_s[j0 + 16 + j]);
                         }
                         rs_stage<16>(v, lane);
                         rs_stage<8>(v, lane);

@@ -885,8 +885,11 @@ def test_selector_tcgen05_path(K, golden, synth):
     # NaN patches give NaN logits, as the reference forward does, and do not disturb their neighbours
     xn = torch.from_numpy(hr).cuda()
     xn[1, 2, 100, 37] = float("nan")
-    ln = sel.logits(xn, algo="umma").cpu().numpy()
-    assert np.isnan(ln[1]).all() and np.array_equal(ln[[0, 2, 3, 4, 5]], lg[[0, 2, 3, 4, 5]])
+    for algo in ("umma", "mma"):
+        ln = sel.logits(xn, algo=algo).cpu().numpy()
+        assert np.isnan(ln[1]).all() and np.isfinite(ln[[0, 2, 3, 4, 5]]).all(), algo
+        if algo == "umma":
+            assert np.array_equal(ln[[0, 2, 3, 4, 5]], lg[[0, 2, 3, 4, 5]])
     # shapes outside the path
     for h, w in ((100, 100), (17, 33), (128, 64), (256, 512)):
         assert K.lib.lib().kmsr_selector_umma_supported(h, w) == 0
