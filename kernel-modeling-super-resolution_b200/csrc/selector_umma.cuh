@@ -113,6 +113,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -138,7 +143,7 @@ struct Shape {
     static constexpr uint32_t SLOT = A_BYTES + B_BYTES;
     static constexpr int NBUF = 8 * COUT <= 512 ? 2 : 1;               // accumulator buffers in TMEM
     static constexpr int TCOLS = 2 * COUT * kTPP;                      // columns per buffer
-    static constexpr uint32_t OUT_BYTES = POOL ? 0u : 128u * COUT * 4;             // one M tile of the output, staged for the TMA store
+    static constexpr uint32_t OUT_BYTES = POOL ? 0u : 2u * 16384u;                 // two staging buffers of 32 channels x 128 pixels for the TMA stores
     static constexpr size_t SMEM = (size_t)kSlots * SLOT + OUT_BYTES + 256 /* barriers */ + COUT * 4 + 4 * 128 * 4 + 1024 /* alignment */;
 };
 
@@ -192,7 +197,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // ------------------------------------------------------------------------------------------ epilogue
         const int row = tid;                                           // row of the M tile = TMEM lane
         const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
-        uint32_t pc = 0;
+        uint32_t pc = 0, unit = 0;
         for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
             const int buf = (int)(pc % Sh::NBUF);
             const long long n = pass / half_tiles;
@@ -207,36 +212,40 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     // 32 channels, 16-byte chunks XOR-swizzled with the row so the per-row stores are conflict free) and written by
                     // one TMA store per 32 channels, which undoes the swizzle -- per-thread 16-byte global stores 128 B apart cost
                     // 2.3 ms per 4096 patches on the first layer
-                    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the staging area
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    // two staging buffers of 32 channels x 128 pixels in rotation, one bulk group per buffer: before a
+                    // buffer is rewritten only the store before the last one has to have read it
+                    const int pix0 = (int)((n * a.tiles + tile0 + t) * 128);
 #pragma unroll 1
-                    for (int j0 = 0; j0 < COUT; j0 += 16) {
-                        float p[16], q[16];
-                        tmem_ld16(p, tcol + j0);
-                        tmem_ld16(q, tcol + COUT + j0);
-                        tmem_ld_wait();
+                    for (int h = 0; h < COUT / 32; ++h, ++unit) {
+                        const uint32_t obuf = ostage + (unit & 1u) * 16384u;
+                        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const uint32_t o0 = __float_as_uint(relu_keep_nan(p[j] + q[j] + bias_s[j0 + j]));
-                            const uint32_t o1 = __float_as_uint(relu_keep_nan(p[j + 1] + q[j + 1] + bias_s[j0 + j + 1]));
-                            const uint32_t o2 = __float_as_uint(relu_keep_nan(p[j + 2] + q[j + 2] + bias_s[j0 + j + 2]));
-                            const uint32_t o3 = __float_as_uint(relu_keep_nan(p[j + 3] + q[j + 3] + bias_s[j0 + j + 3]));
-                            const int c = j0 + j;                                        // first channel of this 16-byte chunk
-                            const uint32_t addr = ostage + (uint32_t)(c >> 5) * 16384u + (uint32_t)row * 128u +
-                                                  ((((uint32_t)(c >> 2) & 7u) ^ ((uint32_t)row & 7u)) << 4);
-                            if (!(UMMA_DBG & 8)) st_shared_v4(addr, o0, o1, o2, o3);
+                        for (int j0 = 0; j0 < 32; j0 += 16) {
+                            float p[16], q[16];
+                            tmem_ld16(p, tcol + 32 * h + j0);
+                            tmem_ld16(q, tcol + COUT + 32 * h + j0);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const int c = 32 * h + j0 + j;                           // first channel of this 16-byte chunk
+                                const uint32_t o0 = __float_as_uint(relu_keep_nan(p[j] + q[j] + bias_s[c]));
+                                const uint32_t o1 = __float_as_uint(relu_keep_nan(p[j + 1] + q[j + 1] + bias_s[c + 1]));
+                                const uint32_t o2 = __float_as_uint(relu_keep_nan(p[j + 2] + q[j + 2] + bias_s[c + 2]));
+                                const uint32_t o3 = __float_as_uint(relu_keep_nan(p[j + 3] + q[j + 3] + bias_s[c + 3]));
+                                const uint32_t addr = obuf + (uint32_t)row * 128u + ((((uint32_t)((j0 + j) >> 2)) ^ ((uint32_t)row & 7u)) << 4);
+                                if (!(UMMA_DBG & 8)) st_shared_v4(addr, o0, o1, o2, o3);
+                            }
                         }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (tid == 0 && !(UMMA_DBG & 8)) {
-                        const int pix0 = (int)((n * a.tiles + tile0 + t) * 128);
-#pragma unroll
-                        for (int h = 0; h < COUT / 32; ++h)
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&omap), "r"(32 * h),
-                                         "r"(pix0), "r"(ostage + (uint32_t)h * 16384u)
-                                         : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (tid == 0) {
+                            if (!(UMMA_DBG & 8))
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&omap), "r"(32 * h),
+                                             "r"(pix0), "r"(obuf)
+                                             : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
                     }
                 } else {
 #pragma unroll 1
@@ -338,8 +347,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                         // the raw fp32 activations ARE the hi operand (the tensor core reads the upper 19 bits): box = 16 channels
                         // x Wo pixels at stride 2 x (128 / Wo) rows at stride 2, zero-filled outside the image = the padding
                         if (lane < kTPP)
-                            tma_load_4d(sa + 2 * lane * kTileBytes, &tmap, 16 * g, dx - 1, 2 * (tile0 + lane) * rows_per_tile + dy - 1, (int)n,
-                                        full_bar(slot));
+                            tma_load_5d(sa + 2 * lane * kTileBytes, &tmap, 16 * g, (dx + 1) & 1, (dx + 1) / 2 - 1,
+                                        2 * (tile0 + lane) * rows_per_tile + dy - 1, (int)n, full_bar(slot));
                         else if (!(UMMA_DBG & 4))
                             bulk_g2s(sa + Sh::A_BYTES, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
                     }
@@ -377,20 +386,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             mbar_arrive(lofull_bar(slot));
         }
     } else {
-        // ------------------------------------------------------------------------------------------ operand builders
-        // Four groups of two warps; group g owns ring slot g and builds every fourth stage of the CTA's flat stage sequence.
-        // A group's loads are issued right after it has published a stage and are consumed one group-iteration later, so
-        // the proxy fence of a stage (a MEMBAR: it waits for every load the thread has in flight) never sees a prefetch;
-        // the global-load latency is hidden by the other three groups instead.
-        //   layers 2 / 3: 16 chunks of 16 bytes per thread and stage: rows R_i = 8 (2 i + w2) + (lane & 7), chunk c = lane >> 3
-        //   first layer:  4 rows R_i = 64 i + t64, 16 scalars each (k = 16 s + e -> (band, dy, dx), compile-time per stage)
-        const int bt = tid - kBuild0, grp = bt >> 6, t64 = bt & 63, w2 = (bt >> 5) & 1;
-        constexpr int NR = CIN == 5 ? 4 : 16;                          // rows per thread
+        // ------------------------------------------------------------------------------------------ operand builders (first layer)
+        // The 5-band [N, 5, H, W] input cannot be fetched as K-major TMA boxes (a 16-byte chunk of the operand is four taps of
+        // one pixel), so threads gather it.  Four groups of two warps; group g owns ring slot g and builds every fourth stage
+        // of the CTA's flat stage sequence.  A group's loads are issued right after it has published a stage and are consumed
+        // one group-iteration later, so the proxy fence of a stage (a MEMBAR: it waits for every load the thread has in
+        // flight) never sees a prefetch; the load latency is hidden by the other three groups instead.
+        // K order: stage s holds the five (band, row) triples T = 5 s + j, j < 5 (band = T / 3, dy = T % 3), k = 3 j + dx,
+        // k = 15 is zero.  A thread owns 4 pixels (R_i = 64 i + t64: a warp = 32 adjacent pixels of one output row); per triple
+        // it loads the aligned pair (2 ox, 2 ox + 1) -- one coalesced 256-byte request per warp -- and takes column 2 ox - 1
+        // from its left neighbour's pair by shuffle when the stage is stored (lane 0 loads it itself): a third of the
+        // load instructions of the scalar gather, which was bound by the L1 tag rate.
+        const int bt = tid - kBuild0, grp = bt >> 6, t64 = bt & 63;
         const uint32_t sa = base + grp * Sh::SLOT;
         const long long my_passes = (a.passes - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
-        float4 rb[16];
-        int offs[NR];                                                  // element offset of input pixel (2 oy - 1, 2 ox - 1) in the patch
-        uint32_t edge = 0;                                             // bit 2 i: row i at oy == 0, bit 2 i + 1: ox == 0
+        float2 pr[4][5];
+        float ex[4][5];
+        int offs[4];                                                   // element offset of input pixel (2 oy - 1, 2 ox) in the patch
+        uint32_t edge = 0;                                             // bit 2 i: pixel i at oy == 0, bit 2 i + 1: ox == 0
         const float* pbase = a.in;
         long long cur = -1;
         auto set_pass = [&](long long pl) {
@@ -401,67 +414,52 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             pbase = a.in + (long long)n * CIN * a.H * a.W;
             edge = 0;
 #pragma unroll
-            for (int i = 0; i < NR; ++i) {
-                const int R = CIN == 5 ? 64 * i + t64 : 8 * (2 * i + w2) + (lane & 7);
-                const int P = tile0 * 128 + R;
+            for (int i = 0; i < 4; ++i) {
+                const int P = tile0 * 128 + 64 * i + t64;
                 const int oy = P / a.Wo, ox = P - oy * a.Wo;
-                offs[i] = CIN == 5 ? (2 * oy - 1) * a.W + (2 * ox - 1) : ((2 * oy - 1) * a.W + (2 * ox - 1)) * CIN + 4 * (lane >> 3);
+                offs[i] = (2 * oy - 1) * a.W + 2 * ox;
                 edge |= ((oy == 0 ? 1u : 0u) | (ox == 0 ? 2u : 0u)) << (2 * i);
             }
         };
         auto load_stage = [&](int s) {
-            if constexpr (CIN == 5) {
 #pragma unroll
-                for (int sc = 0; sc < 3; ++sc)
-                    if (s == sc) {
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float v[16];
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) {
-                                const int k = 16 * sc + e;
-                                const int ch = k / 9, dy = (k % 9) / 3, dx = k % 3;
-                                const bool ok = k < 45 && !((dy == 0) && ((edge >> (2 * i)) & 1u)) && !((dx == 0) && ((edge >> (2 * i + 1)) & 1u));
-                                v[e] = ok ? __ldg(pbase + ((long long)ch * a.H + dy) * a.W + dx + offs[i]) : 0.0f;
-                            }
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) rb[4 * i + c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                        }
-                    }
-            } else {
-                const int tap = s / G, g = s - tap * G;
-                const int dy = tap / 3, dx = tap - 3 * dy;
-                const float* p = pbase + ((long long)dy * a.W + dx) * CIN + 16 * g;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const bool ok = !((dy == 0) && ((edge >> (2 * i)) & 1u)) && !((dx == 0) && ((edge >> (2 * i + 1)) & 1u));
-                    rb[i] = ok ? __ldg(reinterpret_cast<const float4*>(p + offs[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < 5; ++j) {
+                    const int T = 5 * s + j, ch = T / 3, dy = T - 3 * ch;
+                    const bool row_ok = !((dy == 0) && ((edge >> (2 * i)) & 1u));
+                    const float* p = pbase + ((long long)ch * a.H + dy) * a.W + offs[i];
+                    pr[i][j] = row_ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f);
+                    ex[i][j] = (row_ok && lane == 0 && !((edge >> (2 * i + 1)) & 1u)) ? __ldg(p - 1) : 0.0f;
                 }
-            }
-        };
-        // where a chunk goes inside the slot: tile t, part (hi / lo), chunk c, row r -> (2 t + part) 8192 + 2048 c + 128 (r / 8) + 16 (r % 8)
-        auto chunk_dst = [&](int j) -> uint32_t {
-            if constexpr (CIN == 5) {
-                const int R = 64 * (j >> 2) + t64, c = j & 3;
-                return (uint32_t)((2 * (R >> 7)) * kTileBytes + c * kChunkBytes + ((R & 127) >> 3) * 128 + (R & 7) * 16);
-            } else {
-                const int rg = 2 * j + w2;                             // row group of 8 among the pass's 32
-                return (uint32_t)((2 * (rg >> 4)) * kTileBytes + (lane >> 3) * kChunkBytes + (rg & 15) * 128 + (lane & 7) * 16);
-            }
         };
         // TF32 split: the hi tile holds x itself (the tensor core reads its upper 19 bits, i.e. truncates); lo = x minus the
-        // truncated x is exact in fp32 and is rounded to TF32 (ties away, two integer instructions)
+        // truncated x is exact in fp32 and is rounded to TF32 (ties away, two integer instructions).
+        // Where a chunk goes inside the slot: tile t, part (hi / lo), chunk c, row r -> (2 t + part) 8192 + 2048 c + 128 (r / 8) + 16 (r % 8)
         auto store_stage = [&]() {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float4 v = rb[j];
-                const uint32_t d = sa + chunk_dst(j);
+            for (int i = 0; i < 4; ++i) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float left = __shfl_up_sync(0xffffffffu, pr[i][j].y, 1);
+                    v[3 * j] = lane == 0 ? ex[i][j] : left;
+                    v[3 * j + 1] = pr[i][j].x;
+                    v[3 * j + 2] = pr[i][j].y;
+                }
+                v[15] = 0.0f;
+                const int R = 64 * i + t64;
+                const uint32_t d0 = sa + (uint32_t)((2 * (R >> 7)) * kTileBytes + ((R & 127) >> 3) * 128 + (R & 7) * 16);
                 auto lo = [](float x) {
                     const float l = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
                     return (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
                 };
-                st_shared_v4(d, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-                st_shared_v4(d + kTileBytes, lo(v.x), lo(v.y), lo(v.z), lo(v.w));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t d = d0 + c * kChunkBytes;
+                    st_shared_v4(d, __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+                    st_shared_v4(d + kTileBytes, lo(v[4 * c]), lo(v[4 * c + 1]), lo(v[4 * c + 2]), lo(v[4 * c + 3]));
+                }
             }
         };
         // flat stage sequence of this CTA: (local pass pl, stage s), this group takes every fourth
@@ -509,11 +507,11 @@ int launch_conv_umma(const ConvUArgs& a, long long N, int sms, cudaStream_t st) 
         // group of one tap: 16 channels x Wo pixels (every second column) x 128 / Wo rows (every second row), 64-byte swizzle
         EncodeTiledFn enc = get_tensor_map_encoder();
         KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled is not available");
-        cuuint64_t gdim[4] = {(cuuint64_t)CIN, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)N};
-        cuuint64_t gstr[3] = {(cuuint64_t)CIN * 4, (cuuint64_t)a.W * CIN * 4, (cuuint64_t)a.H * a.W * CIN * 4};
-        cuuint32_t box[4] = {16, (cuuint32_t)(2 * a.Wo), (cuuint32_t)(2 * (128 / a.Wo)), 1};
-        cuuint32_t estr[4] = {1, 2, 2, 1};
-        CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        cuuint64_t gdim[5] = {(cuuint64_t)CIN, 2, (cuuint64_t)(a.W / 2), (cuuint64_t)a.H, (cuuint64_t)N};
+        cuuint64_t gstr[4] = {(cuuint64_t)CIN * 4, (cuuint64_t)CIN * 8, (cuuint64_t)a.W * CIN * 4, (cuuint64_t)a.H * a.W * CIN * 4};
+        cuuint32_t box[5] = {16, 1, (cuuint32_t)a.Wo, (cuuint32_t)(2 * (128 / a.Wo)), 1};
+        cuuint32_t estr[5] = {1, 1, 1, 2, 1};
+        CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)a.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
     }

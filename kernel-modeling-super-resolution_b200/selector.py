@@ -123,14 +123,15 @@ class Selector:
         float32 [stage][4 chunks][2 cout / 8][8][4] -- per stage of 16 values of K the shared-memory image of the operand
         [B_hi ; B_lo] in the K-major canonical layout without swizzle (core matrix = 8 rows x 16 bytes).  Rows < cout hold the
         TF32 hi part of output channel `row`, rows >= cout the lo part of channel `row - cout`.  K runs tap-major in groups
-        of 16 input channels (stage = tap * cin / 16 + group, k = 16 group + 4 chunk + e); the 5-channel first layer uses
-        k = 16 stage + 4 chunk + e = 9 band + tap, zero from 45 to 47."""
+        of 16 input channels (stage = tap * cin / 16 + group, k = 16 group + 4 chunk + e); the 5-channel first layer puts the
+        five (band, kernel row) triples T = 5 stage + j = 3 band + dy at k = 3 j + dx of a stage and zero at k = 15."""
         cout, cin = wf.shape[0], wf.shape[1]
         w9 = wf.reshape(cout, cin, 9)
         if cin == 5:
             stages = 3
-            flat = np.zeros((cout, 48), dtype=np.float32)
-            flat[:, :45] = w9.reshape(cout, 45)                                   # k = 9 band + tap
+            flat = np.zeros((cout, 3, 16), dtype=np.float32)
+            flat[:, :, :15] = w9.reshape(cout, 3, 15)              # stage s: triples T = 5 s + j = 3 band + dy, k = 3 j + dx; k = 15: zero
+            flat = flat.reshape(cout, 48)
         else:
             assert cin % 16 == 0, cin
             stages = 9 * (cin // 16)

@@ -47,8 +47,8 @@ static std::vector<float> pack_weights(const std::vector<float>& w, int cin, int
                     const int co = nn % cout;
                     float v = 0.0f;
                     if (cin == 5) {
-                        const int k = 16 * s + 4 * c + e;
-                        if (k < 45) v = w[((size_t)co * cin + k / 9) * 9 + k % 9];
+                        const int kk = 4 * c + e;                 // k = 3 j + dx of triple T = 5 s + j (band = T / 3, dy = T % 3); 15: zero
+                        if (kk < 15) { const int T = 5 * s + kk / 3; v = w[((size_t)co * cin + T / 3) * 9 + (T % 3) * 3 + kk % 3]; }
                     } else {
                         const int tap = s / G, g = s % G, ci = 16 * g + 4 * c + e;
                         v = w[((size_t)co * cin + ci) * 9 + tap];

@@ -347,7 +347,7 @@ def test_selector_tcgen05_weight_stages_reproduce_the_reference_forward(golden):
     [stage][4 chunks][2 cout / 8][8][4] are read back the way conv_umma_kernel's descriptors address them (K-major
     canonical layout without swizzle: row n, value k of a stage at chunk k // 4, row group n // 8, row n % 8, element
     k % 4; rows < cout = TF32 hi part, rows >= cout = lo part; stage = tap * cin / 16 + group, the first layer
-    k = 9 band + tap) and a float64 forward through hi + lo must give the logits of the torch fp32 forward."""
+    15 taps of five (band, kernel row) triples per stage and a zero) and a float64 forward through hi + lo must give the logits of the torch fp32 forward."""
     from kmsr_b200.selector import Selector
     z = golden("selector.npz")
     sel = Selector.from_npz(z, "cpu")
@@ -359,8 +359,9 @@ def test_selector_tcgen05_weight_stages_reproduce_the_reference_forward(golden):
         rows = img.transpose(2, 3, 0, 1, 4).reshape(2 * cout, stages * 16).astype(np.float64)   # [row][k]
         both = rows[:cout] + rows[cout:]
         if cin == 5:
-            assert stages == 3 and np.abs(both[:, 45:]).max() == 0.0
-            return both[:, :45].reshape(cout, 5, 3, 3)
+            st = both.reshape(cout, 3, 16)
+            assert stages == 3 and np.abs(st[:, :, 15]).max() == 0.0
+            return st[:, :, :15].reshape(cout, 5, 3, 3)
         assert stages == 9 * (cin // 16)
         return both.reshape(cout, 9, cin).transpose(0, 2, 1).reshape(cout, cin, 3, 3)
 
