@@ -36,7 +36,8 @@ constexpr int kEpiWarps = 4, kBuildWarps = 8;
 constexpr int kBuildThreads = 32 * kBuildWarps;
 constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1;
 constexpr int kBuild0 = 32 * (kEpiWarps + 2);                  // first builder thread
-constexpr int kThreads = kBuild0 + kBuildThreads;              // 448
+constexpr int kMma2Warp = kEpiWarps + 2 + kBuildWarps;         // second MMA issuer (the pass's second M tile)
+constexpr int kThreads = 32 * (kMma2Warp + 1);                 // 480
 #ifndef UMMA_SLOTS
 #define UMMA_SLOTS 4
 #endif
@@ -174,10 +175,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             // first layer: the slot's builder group after its stores + the weight copy's expect_tx; others: the producer's expect_tx
             mbar_init(full_bar(s), TMA ? 1 : kBuildThreads / kSlots + 1);
             mbar_init(lofull_bar(s), kBuildThreads);                   // every builder after its lo stores
-            mbar_init(empty_bar(s), 1);                                // one tcgen05.commit
+            mbar_init(empty_bar(s), kTPP);                             // one tcgen05.commit per MMA issuer
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(tfull_bar(b), 1);
+            mbar_init(tfull_bar(b), kTPP);
             mbar_init(tempty_bar(b), 32 * kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -288,37 +289,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             }
         }
         if (!POOL && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kMmaWarp || warp == kMma2Warp) {
         // ------------------------------------------------------------------------------------------ MMA issue
+        // One thread per M tile of the pass: the MMAs here are small (32-128 clocks of tensor time each) and a thread needs
+        // ~50-90 clocks to issue one (uniform-register descriptor moves, elect, branch), so a single issuer was the limiter
+        // (ncu: 80 % of its samples in the issue sequence).  Descriptors are the slot-0 descriptor plus constants.
         if (lane == 0) {
+            const int t = warp == kMmaWarp ? 0 : 1;
             constexpr uint32_t idesc_cat = idesc_tf32(2 * COUT), idesc_one = idesc_tf32(COUT);
+            constexpr uint64_t kLo = kTileBytes >> 4;                                           // hi tile -> lo tile
+            constexpr uint64_t kJA = TMA ? (32 >> 4) : ((2 * kChunkBytes) >> 4);              // second k-step of a stage, A
+            constexpr uint64_t kJB = (2 * Sh::B_LBO) >> 4;                                      // ... and B
+            const uint64_t a0 = (TMA ? smem_desc_sw64(base) : smem_desc(base, kChunkBytes, 128)) + (uint64_t)((t * 2 * kTileBytes) >> 4);
+            const uint64_t b0 = smem_desc(base + Sh::A_BYTES, Sh::B_LBO, 128);
             uint32_t it = 0, pc = 0;
             for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
                 const int buf = (int)(pc % Sh::NBUF);
                 mbar_wait(tempty_bar(buf), ((pc / Sh::NBUF) & 1u) ^ 1u);
                 tc_fence_after();
+                const uint32_t dcol = tm + (uint32_t)(buf * Sh::TCOLS + t * 2 * COUT);
 #pragma unroll 1
                 for (int s = 0; s < S; ++s, ++it) {
                     const int slot = (int)(it % kSlots);
                     mbar_wait(full_bar(slot), (it / kSlots) & 1u);
                     if constexpr (TMA) mbar_wait(lofull_bar(slot), (it / kSlots) & 1u);
                     tc_fence_after();
-                    const uint32_t sa = base + slot * Sh::SLOT, sb = sa + Sh::A_BYTES;
-#pragma unroll
-                    for (int t = 0; t < kTPP; ++t) {
-                        const uint32_t dcol = tm + (uint32_t)(buf * Sh::TCOLS + t * 2 * COUT);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint64_t bd = smem_desc(sb + j * 2 * Sh::B_LBO, Sh::B_LBO, 128);
-                            const uint64_t ahi = TMA ? smem_desc_sw64(sa + (t * 2 + 0) * kTileBytes + j * 32)
-                                                     : smem_desc(sa + (t * 2 + 0) * kTileBytes + j * 2 * kChunkBytes, kChunkBytes, 128);
-                            const uint64_t alo = TMA ? smem_desc_sw64(sa + (t * 2 + 1) * kTileBytes + j * 32)
-                                                     : smem_desc(sa + (t * 2 + 1) * kTileBytes + j * 2 * kChunkBytes, kChunkBytes, 128);
-                            if (!(UMMA_DBG & 1)) {
-                                mma_tf32_ss(dcol, ahi, bd, idesc_cat, (s | j) != 0);
-                                mma_tf32_ss(dcol, alo, bd, idesc_one, 1u);
-                            }
-                        }
+                    const uint64_t so = (uint64_t)((slot * Sh::SLOT) >> 4);
+                    const uint64_t ahi = a0 + so, bd = b0 + so;
+                    if (!(UMMA_DBG & 1)) {
+                        mma_tf32_ss(dcol, ahi, bd, idesc_cat, s != 0);
+                        mma_tf32_ss(dcol, ahi + kLo, bd, idesc_one, 1u);
+                        mma_tf32_ss(dcol, ahi + kJA, bd + kJB, idesc_cat, 1u);
+                        mma_tf32_ss(dcol, ahi + kJA + kLo, bd + kJB, idesc_one, 1u);
                     }
                     mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot
                 }
