@@ -138,14 +138,21 @@ template <int CIN, int COUT, bool POOL>
 struct Shape {
     static constexpr int G = CIN >= 16 ? CIN / 16 : 1;                 // channel groups of 16 per tap
     static constexpr int S = CIN == 5 ? 3 : 9 * G;                     // stages per pass (first layer: K = 45 -> 48)
-    static constexpr uint32_t A_BYTES = kTPP * 2 * kTileBytes;         // hi and lo tiles of both M tiles
     static constexpr uint32_t B_LBO = 32u * COUT;                      // (2 COUT / 8) row groups x 128 B
     static constexpr uint32_t B_BYTES = 4 * B_LBO;
-    static constexpr uint32_t SLOT = A_BYTES + B_BYTES;
+    // first layer: one ring of NH slots [hi 0 | lo 0 | hi 1 | lo 1 | B]; layers 2 / 3: a deep ring of TMA landing slots
+    // [hi 0 | hi 1 | B] and a short ring of lo slots [lo 0 | lo 1] that live only between the builders and the MMAs
+    static constexpr bool SPLIT = CIN != 5;
+    static constexpr uint32_t HT = SPLIT ? kTileBytes : 2 * kTileBytes;     // hi tile t at t * HT inside its slot
+    static constexpr uint32_t BOFF = kTPP * HT;                              // weights behind the tiles
+    static constexpr uint32_t SLOT = BOFF + B_BYTES;
+    static constexpr uint32_t LSLOT = kTPP * kTileBytes;
+    static constexpr int NH = !SPLIT ? 4 : (COUT <= 64 ? 6 : 5);
+    static constexpr int NL = !SPLIT ? 0 : (COUT <= 64 ? 3 : 2);
     static constexpr int NBUF = 8 * COUT <= 512 ? 2 : 1;               // accumulator buffers in TMEM
     static constexpr int TCOLS = 2 * COUT * kTPP;                      // columns per buffer
     static constexpr uint32_t OUT_BYTES = POOL ? 0u : 2u * 16384u;                 // two staging buffers of 32 channels x 128 pixels for the TMA stores
-    static constexpr size_t SMEM = (size_t)kSlots * SLOT + OUT_BYTES + 256 /* barriers */ + COUT * 4 + 4 * 128 * 4 + 1024 /* alignment */;
+    static constexpr size_t SMEM = (size_t)NH * SLOT + (size_t)NL * LSLOT + OUT_BYTES + 512 /* barriers */ + COUT * 4 + (POOL ? 4 * 128 * 4 : 0) + 1024 /* alignment */;
 };
 
 template <int CIN, int COUT, bool POOL>
@@ -158,24 +165,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const uint32_t raw = smem_u32(umma_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* basep = umma_smem_raw + (base - raw);
-    const uint32_t ostage = base + kSlots * Sh::SLOT;                  // [COUT / 32][128 rows][128 B], 128-byte swizzle (store epilogue)
+    constexpr int NH = Sh::NH, NL = Sh::NL > 0 ? Sh::NL : 1;
+    const uint32_t lobase = base + NH * Sh::SLOT;                      // lo ring (layers 2 / 3)
+    const uint32_t ostage = lobase + Sh::NL * Sh::LSLOT;               // 2 x [128 rows][128 B], 128-byte swizzle (store epilogue)
     const uint32_t bars = ostage + Sh::OUT_BYTES;                      // full[4] empty[4] tfull[2] tempty[2] | tmem holder | lofull[4]
     auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };      // 8 barriers each: full, empty, lofull, loempty, tfull | tempty (4 + 4)
     auto lofull_bar = [&](int s) { return bars + 128u + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 32u + 8u * s; };
-    auto tfull_bar = [&](int b) { return bars + 64u + 8u * b; };
-    auto tempty_bar = [&](int b) { return bars + 80u + 8u * b; };
-    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(basep + kSlots * Sh::SLOT + Sh::OUT_BYTES + 96);
-    float* bias_s = reinterpret_cast<float*>(basep + kSlots * Sh::SLOT + Sh::OUT_BYTES + 256);
+    auto loempty_bar = [&](int s) { return bars + 192u + 8u * s; };
+    auto tfull_bar = [&](int b) { return bars + 256u + 8u * b; };
+    auto tempty_bar = [&](int b) { return bars + 288u + 8u * b; };
+    volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(basep + (ostage - base) + Sh::OUT_BYTES + 320);
+    float* bias_s = reinterpret_cast<float*>(basep + (ostage - base) + Sh::OUT_BYTES + 512);
     float* red_s = bias_s + COUT;                                      // [4 warps][128] (pooling only)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < kSlots; ++s) {
+        for (int s = 0; s < NH; ++s) {
             // first layer: the slot's builder group after its stores + the weight copy's expect_tx; others: the producer's expect_tx
-            mbar_init(full_bar(s), TMA ? 1 : kBuildThreads / kSlots + 1);
-            mbar_init(lofull_bar(s), kBuildThreads);                   // every builder after its lo stores
+            mbar_init(full_bar(s), TMA ? 1 : kBuildThreads / NH + 1);
             mbar_init(empty_bar(s), kTPP);                             // one tcgen05.commit per MMA issuer
+        }
+        for (int s = 0; s < NL; ++s) {
+            mbar_init(lofull_bar(s), kBuildThreads);                   // every builder after its lo stores
+            mbar_init(loempty_bar(s), kTPP);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), kTPP);
@@ -297,11 +310,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         if (lane == 0) {
             const int t = warp == kMmaWarp ? 0 : 1;
             constexpr uint32_t idesc_cat = idesc_tf32(2 * COUT), idesc_one = idesc_tf32(COUT);
-            constexpr uint64_t kLo = kTileBytes >> 4;                                           // hi tile -> lo tile
             constexpr uint64_t kJA = TMA ? (32 >> 4) : ((2 * kChunkBytes) >> 4);              // second k-step of a stage, A
             constexpr uint64_t kJB = (2 * Sh::B_LBO) >> 4;                                      // ... and B
-            const uint64_t a0 = (TMA ? smem_desc_sw64(base) : smem_desc(base, kChunkBytes, 128)) + (uint64_t)((t * 2 * kTileBytes) >> 4);
-            const uint64_t b0 = smem_desc(base + Sh::A_BYTES, Sh::B_LBO, 128);
+            const uint64_t a0 = (TMA ? smem_desc_sw64(base) : smem_desc(base, kChunkBytes, 128)) + (uint64_t)((t * Sh::HT) >> 4);
+            const uint64_t l0 = TMA ? smem_desc_sw64(lobase) + (uint64_t)((t * kTileBytes) >> 4) : a0 + (kTileBytes >> 4);
+            const uint64_t b0 = smem_desc(base + Sh::BOFF, Sh::B_LBO, 128);
             uint32_t it = 0, pc = 0;
             for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
                 const int buf = (int)(pc % Sh::NBUF);
@@ -310,19 +323,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 const uint32_t dcol = tm + (uint32_t)(buf * Sh::TCOLS + t * 2 * COUT);
 #pragma unroll 1
                 for (int s = 0; s < S; ++s, ++it) {
-                    const int slot = (int)(it % kSlots);
-                    mbar_wait(full_bar(slot), (it / kSlots) & 1u);
-                    if constexpr (TMA) mbar_wait(lofull_bar(slot), (it / kSlots) & 1u);
+                    const int slot = (int)(it % NH), ls = (int)(it % NL);
+                    mbar_wait(full_bar(slot), (it / NH) & 1u);
+                    if constexpr (TMA) mbar_wait(lofull_bar(ls), (it / NL) & 1u);
                     tc_fence_after();
                     const uint64_t so = (uint64_t)((slot * Sh::SLOT) >> 4);
                     const uint64_t ahi = a0 + so, bd = b0 + so;
+                    const uint64_t alo = TMA ? l0 + (uint64_t)((ls * Sh::LSLOT) >> 4) : l0 + so;
                     if (!(UMMA_DBG & 1)) {
                         mma_tf32_ss(dcol, ahi, bd, idesc_cat, s != 0);
-                        mma_tf32_ss(dcol, ahi + kLo, bd, idesc_one, 1u);
+                        mma_tf32_ss(dcol, alo, bd, idesc_one, 1u);
                         mma_tf32_ss(dcol, ahi + kJA, bd + kJB, idesc_cat, 1u);
-                        mma_tf32_ss(dcol, ahi + kJA + kLo, bd + kJB, idesc_one, 1u);
+                        mma_tf32_ss(dcol, alo + kJA, bd + kJB, idesc_one, 1u);
                     }
                     mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot
+                    if constexpr (TMA) mma_commit(loempty_bar(ls));
                 }
                 mma_commit(tfull_bar(buf));                            // ... and once the accumulators are final
             }
@@ -340,19 +355,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     const int tile0 = (int)(pass - n * half_tiles) * kTPP;
 #pragma unroll 1
                     for (int s = 0; s < S; ++s, ++it) {
-                        const int slot = (int)(it % kSlots);
+                        const int slot = (int)(it % NH);
                         const uint32_t sa = base + slot * Sh::SLOT;
                         const int tap = s / G, g = s - tap * G;
                         const int dy = tap / 3, dx = tap - 3 * dy;
-                        mbar_wait(empty_bar(slot), ((it / kSlots) & 1u) ^ 1u);
+                        mbar_wait(empty_bar(slot), ((it / NH) & 1u) ^ 1u);
                         if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), kTPP * kTileBytes + ((UMMA_DBG & 4) ? 0u : Sh::B_BYTES));
                         // the raw fp32 activations ARE the hi operand (the tensor core reads the upper 19 bits): box = 16 channels
                         // x Wo pixels at stride 2 x (128 / Wo) rows at stride 2, zero-filled outside the image = the padding
                         if (lane < kTPP)
-                            tma_load_5d(sa + 2 * lane * kTileBytes, &tmap, 16 * g, (dx + 1) & 1, (dx + 1) / 2 - 1,
+                            tma_load_5d(sa + lane * kTileBytes, &tmap, 16 * g, (dx + 1) & 1, (dx + 1) / 2 - 1,
                                         2 * (tile0 + lane) * rows_per_tile + dy - 1, (int)n, full_bar(slot));
                         else if (!(UMMA_DBG & 4))
-                            bulk_g2s(sa + Sh::A_BYTES, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
+                            bulk_g2s(sa + Sh::BOFF, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
                     }
                 }
             }
@@ -367,25 +382,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const long long total = my_passes * S;
         uint32_t it = 0;
         for (long long q = 0; q < total; ++q, ++it) {
-            const int slot = (int)(it % kSlots);
-            const uint32_t sa = base + slot * Sh::SLOT;
-            mbar_wait(full_bar(slot), (it / kSlots) & 1u);
+            const int slot = (int)(it % NH), ls = (int)(it % NL);
+            const uint32_t sa = base + slot * Sh::SLOT, sl = lobase + ls * Sh::LSLOT;
+            mbar_wait(full_bar(slot), (it / NH) & 1u);
+            mbar_wait(loempty_bar(ls), ((it / NL) & 1u) ^ 1u);
             if (!(UMMA_DBG & 2)) {
 #pragma unroll
                 for (int i = 0; i < (int)(kTPP * kTileBytes / 16 / kBuildThreads); ++i) {
-                    const uint32_t chunk = (uint32_t)bt + (uint32_t)i * kBuildThreads;
-                    const uint32_t addr = sa + (chunk >> 9) * 2 * kTileBytes + (chunk & 511u) * 16u;
+                    const uint32_t off = ((uint32_t)bt + (uint32_t)i * kBuildThreads) * 16u;     // the two hi tiles are contiguous, so are the lo tiles
                     uint32_t x0, x1, x2, x3;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sa + off));
                     auto lo = [](uint32_t x) {
                         const float l = __uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u);
                         return (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
                     };
-                    st_shared_v4(addr + kTileBytes, lo(x0), lo(x1), lo(x2), lo(x3));
+                    st_shared_v4(sl + off, lo(x0), lo(x1), lo(x2), lo(x3));
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
-            mbar_arrive(lofull_bar(slot));
+            mbar_arrive(lofull_bar(ls));
         }
     } else {
         // ------------------------------------------------------------------------------------------ operand builders (first layer)
@@ -478,13 +493,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 if (UMMA_DBG & 4) mbar_arrive(full_bar(grp));
                 else {
                     mbar_arrive_expect_tx(full_bar(grp), Sh::B_BYTES);
-                    bulk_g2s(sa + Sh::A_BYTES, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(grp));
+                    bulk_g2s(sa + Sh::BOFF, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(grp));
                 }
             }
             if (!(UMMA_DBG & 2)) store_stage();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
             mbar_arrive(full_bar(grp));
-            s += kSlots;
+            s += NH;
             while (s >= S) { s -= S; ++pl; }
             if (pl < my_passes && !(UMMA_DBG & 2)) {
                 if (pl != cur) set_pass(pl);
