@@ -493,7 +493,9 @@ def main():
                                  c5_algos="", c5_cells=[(31, 64, 8), (21, 64, 8), (15, 256, 4), (13, 256, 2), (31, 256, 2),
                                                         (11, 512, 8), (13, 512, 8)])
         configs = {}
-        for name, f in (("config3", rc.config3), ("config4", rc.config4)) + ((("config5", rc.config5),) if world == 1 else ()):
+        ns_.sel_patches = 4096
+        for name, f in (("config3", rc.config3), ("config4", rc.config4), ("f2_selector", rc.selector_pick)) + \
+                ((("config5", rc.config5),) if world == 1 else ()):
             try:
                 t0 = time.perf_counter()
                 r = f(ns_, rank, world, dev)

@@ -407,6 +407,39 @@ def config5(args, rank, world, dev):
             "rows": rows, "parity": par, "bar": 1e-5}
 
 
+def selector_pick(args, rank, world, dev):
+    """Row f2 (SelectorNet, train_gemini.py:14-39): the learned pick of `args.sel_patches` patches through the tcgen05
+    kernels, the mma.sync kernels and the fp32 library forward (TF32 off), next to the fused degrade launch it feeds;
+    picks compared with the library forward's and with the reference module's golden logits."""
+    from kmsr_b200.selector import Selector
+    z = np.load(os.path.join(ROOT, "tests", "golden", "selector.npz"))
+    sel = Selector.from_npz(z, dev)
+    kb, sb = bank()
+    n = int(getattr(args, "sel_patches", 4096))
+    hr = synth_hr_device(n, 4242 + rank, dev)
+    pb = ops.prepare_kernels(torch.from_numpy(kb).to(dev), 8)
+    ms_umma = timed(lambda: sel.logits(hr, algo="umma"), args.reps, world)
+    ms_mma = timed(lambda: sel.logits(hr, algo="mma"), args.reps, world)
+    a = sel.logits(hr, algo="umma")
+    b = sel.logits_library(hr)
+    ms_lib = timed(lambda: sel.logits_library(hr), 1, world)
+    kidx = a.argmax(1).to(torch.int32)
+    ms_deg = timed(lambda: ops.degrade_batch(hr, pb, kidx=kidx, factor=8), args.reps, world)
+    scale = float(b.abs().max())
+    hg = np.concatenate([synth.make_hr(4, 5100, "textured"), synth.make_hr(2, 5101, "water")])
+    lg = sel.logits(torch.from_numpy(hg).to(dev), algo="umma").cpu().numpy()
+    flop = 2.0 * n * (128 * 128 * 32 * 45 + 64 * 64 * 64 * 288 + 32 * 32 * 128 * 576)
+    return {"row": "f2", "workload": f"SelectorNet pick of {n} patches [5,256,256] per GPU (3 convolutions + pooling + linear layer)",
+            "algo": "tcgen05 (kind::tf32, TMEM accumulators, 3xTF32 split as two MMAs per k-step)",
+            "ms_tcgen05": ms_umma, "ms_mma_sync": ms_mma, "ms_library_fp32": ms_lib, "ms_fused_degrade": ms_deg,
+            "patches_per_s": n * world / (ms_umma * 1e-3), "useful_tflops": flop / (ms_umma * 1e-3) / 1e12,
+            "tensor_tflops_3x": 3 * flop / (ms_umma * 1e-3) / 1e12,
+            "logits_vs_library_over_scale": float((a - b).abs().max()) / scale,
+            "picks_equal_library": bool(torch.equal(a.argmax(1), b.argmax(1))),
+            "golden_logits_over_scale": float(np.abs(lg - z["logits"][:6]).max() / np.abs(z["logits"]).max()),
+            "golden_picks_equal": bool(np.array_equal(lg.argmax(1), z["argmax"][:6])), "bar": 1e-4}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,3,4,5")
@@ -423,7 +456,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     torch.set_num_threads(os.cpu_count() or 1)
-    fns = {1: config1, 3: config3, 4: config4, 5: config5}
+    fns = {1: config1, 3: config3, 4: config4, 5: config5, 2: selector_pick}      # 2 = row f2's selector leg (config 2 itself is bench.py)
     results = []
     for c in [int(x) for x in args.configs.split(",")]:
         if world > 1 and c in (1, 5):
