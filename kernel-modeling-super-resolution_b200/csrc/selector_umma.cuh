@@ -216,7 +216,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             const int buf = (int)(pc % Sh::NBUF);
             const long long n = pass / half_tiles;
             const int tile0 = (int)(pass - n * half_tiles) * kTPP;
-            mbar_wait(tfull_bar(buf), (pc / Sh::NBUF) & 1u);
+            mbar_wait_relaxed(tfull_bar(buf), (pc / Sh::NBUF) & 1u);
             tc_fence_after();
 #pragma unroll 1
             for (int t = 0; t < kTPP; ++t) {
@@ -384,8 +384,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         for (long long q = 0; q < total; ++q, ++it) {
             const int slot = (int)(it % NH), ls = (int)(it % NL);
             const uint32_t sa = base + slot * Sh::SLOT, sl = lobase + ls * Sh::LSLOT;
-            mbar_wait(full_bar(slot), (it / NH) & 1u);
-            mbar_wait(loempty_bar(ls), ((it / NL) & 1u) ^ 1u);
+            mbar_wait_relaxed(full_bar(slot), (it / NH) & 1u);
+            mbar_wait_relaxed(loempty_bar(ls), ((it / NL) & 1u) ^ 1u);
             if (!(UMMA_DBG & 2)) {
 #pragma unroll
                 for (int i = 0; i < (int)(kTPP * kTileBytes / 16 / kBuildThreads); ++i) {
@@ -438,16 +438,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 edge |= ((oy == 0 ? 1u : 0u) | (ox == 0 ? 2u : 0u)) << (2 * i);
             }
         };
+        const long long HW = (long long)a.H * a.W;
         auto load_stage = [&](int s) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int sc = 0; sc < 3; ++sc)                             // the stage as a compile-time constant: (band, dy) of a triple fold
+                if (s == sc) {
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const int T = 5 * s + j, ch = T / 3, dy = T - 3 * ch;
-                    const bool row_ok = !((dy == 0) && ((edge >> (2 * i)) & 1u));
-                    const float* p = pbase + ((long long)ch * a.H + dy) * a.W + offs[i];
-                    pr[i][j] = row_ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f);
-                    ex[i][j] = (row_ok && lane == 0 && !((edge >> (2 * i + 1)) & 1u)) ? __ldg(p - 1) : 0.0f;
+                    for (int i = 0; i < 4; ++i) {
+                        const bool top = (edge >> (2 * i)) & 1u, left_ok = lane == 0 && !((edge >> (2 * i + 1)) & 1u);
+                        const float* p0 = pbase + offs[i];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) {
+                            constexpr int kDummy = 0;
+                            (void)kDummy;
+                            const int T = 5 * sc + j, ch = T / 3, dy = T - 3 * ch;
+                            const bool row_ok = !(dy == 0 && top);
+                            const float* p = p0 + ch * HW + dy * a.W;
+                            pr[i][j] = row_ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f);
+                            ex[i][j] = (row_ok && left_ok) ? __ldg(p - 1) : 0.0f;
+                        }
+                    }
                 }
         };
         // TF32 split: the hi tile holds x itself (the tensor core reads its upper 19 bits, i.e. truncates); lo = x minus the
@@ -488,7 +498,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             load_stage(s);
         }
         for (uint32_t m = 0; pl < my_passes; ++m) {
-            mbar_wait(empty_bar(grp), (m & 1u) ^ 1u);
+            mbar_wait_relaxed(empty_bar(grp), (m & 1u) ^ 1u);
             if (t64 == 0) {
                 if (UMMA_DBG & 4) mbar_arrive(full_bar(grp));
                 else {
