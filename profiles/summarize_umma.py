@@ -62,7 +62,8 @@ def main():
     # split the SASS into role regions at the role-defining instructions
     marks = {"epilogue": "LDTM", "mma issue": "UTCHMMA", "tma producer": "UTMALDG"}
     first = {k: next((n for n, r in enumerate(data) if m in r[ix["Source"]]), None) for k, m in marks.items()}
-    lines = [f"{out['kernel']}", f"gpu__time_duration {out.get('gpu__time_duration.sum', {}).get('value')} ms", ""]
+    t = out.get("gpu__time_duration.sum", {})
+    lines = [f"{out['kernel']}", f"gpu__time_duration {t.get('value')} {t.get('unit')}", ""]
     tot = sum(int(r[ix["# Samples"]]) for r in data)
     lines.append(f"warp-stall samples: {tot} in total; by reason (all warps):")
     agg = {k: sum(int(r[ix[k]]) for r in data) for k in reasons}
