@@ -1,24 +1,33 @@
 // selector_umma.cuh -- SelectorNet convolutions (muti_kernel/train_gemini.py:14-39) on the 5th-generation tensor cores:
-// `tcgen05.mma.kind::tf32` with the accumulators in tensor memory, SURVEY.md 8f row f2, round 2.
+// `tcgen05.mma.kind::tf32` with the accumulators in tensor memory, SURVEY.md 8f row f2, round 2.  DESIGN.md 4.8.
 //
 // A 3x3 / stride-2 / pad-1 convolution is the GEMM  D[pixel, cout] = sum_k A[pixel, k] B[cout, k],  k = (tap, cin).
 // One MMA tile is 128 output pixels (raster order inside a patch) x COUT channels; K is walked in stages of 16 (two MMA
 // k-steps of 8).  fp32-level accuracy comes from the 3xTF32 split, arranged so that two MMAs do the work of three:
 //     D[:, 0:2C]  += A_hi x [B_hi ; B_lo]^T      (N = 2 COUT: hi*hi in columns 0..C-1, hi*lo in columns C..2C-1)
 //     D[:, 0:C]   += A_lo x  B_hi^T              (N = COUT, accumulated onto the hi*hi columns)
-// and the epilogue adds the two column halves.  Both operands sit in shared memory in the K-major canonical layout
-// without swizzle (core matrix = 8 rows x 16 bytes, contiguous), which is what lets plain threads build the im2col
-// operand: a 16-byte chunk = 4 consecutive input channels of one tap of one output pixel (channel-last activations).
+// and the epilogue adds the two column halves.
 //
-// Warp roles (416 threads, one persistent CTA per SM):
-//   warps 0-3   epilogue: tcgen05.ld of the tile (TMEM lane quadrant = warp), halves added, + bias, ReLU, then either
-//               the channel-last store or -- last layer -- the per-tile channel sums (shuffle reduce-scatter, fixed
-//               order, deterministic) that pool_fc_kernel turns into logits
-//   warp  4     one thread issues the MMAs and the commits that release a ring slot / publish an accumulator buffer
-//   warps 5-12  builders: global (L2) -> registers -> TF32 hi / lo split -> canonical operand tiles in a 4-slot ring; loads
-//               run two stages ahead of the stores (register ring of three); one of them streams the stage's weights, already
-//               laid out as the shared-memory image by the host, with one bulk copy
+// The tensor core truncates an fp32 operand to TF32 (scratch/umma_round_probe.cu), so the raw activations ARE A_hi and
+// A_lo = rna_tf32(x - trunc_tf32(x)).  Layers 2 / 3 (channel-last activations): A_hi arrives as TMA boxes in the operand
+// layout itself -- 16 channels x Wo pixels (every second column) x 128 / Wo rows (every second row), 64-byte swizzle,
+// zero fill outside the image = the padding; the descriptor is K-major SWIZZLE_64B.  A_lo is built from the landed tile
+// by the builder warps (the lo tile mirrors the hi tile byte for byte).  The weights [B_hi ; B_lo] stream per stage as one
+// bulk copy of the host-built shared-memory image (K-major canonical layout without swizzle).  First layer ([N, 5, H, W]
+// input): a 16-byte operand chunk is four taps of one pixel, which no box produces: threads gather hi and lo tiles.
+//
+// Warp roles (480 threads, one persistent CTA per SM):
+//   warps 0-3   epilogue: tcgen05.ld of the tile (TMEM lane quadrant = warp), halves added, + bias, ReLU, then either the
+//               tile staged in swizzled shared memory and written by TMA stores (two staging buffers in rotation) or --
+//               last layer -- the per-tile channel sums (shuffle reduce-scatter, fixed order, deterministic) that
+//               pool_fc_kernel turns into logits
+//   warps 4, 14 one thread each issues the MMAs of one M tile of the pass and the commits that release ring slots /
+//               publish the accumulator buffer
+//   warp  5     layers 2 / 3: TMA producer (three lanes: the two tiles' boxes and the weight stage)
+//   warps 6-13  operand builders: lo tiles from the landed hi tiles (layers 2 / 3), or the gather of both tiles (layer 1:
+//               four groups of two warps, one ring slot each)
 // A pass = two M tiles sharing every weight stage; accumulators are double-buffered in TMEM when 8 COUT <= 512 columns.
+// Rings: layers 2 / 3 a deep ring of TMA landing slots [hi 0 | hi 1 | B] and a short ring of lo slots; layer 1 one ring.
 #pragma once
 #include <string.h>
 
@@ -38,10 +47,6 @@ constexpr int kMmaWarp = kEpiWarps, kTmaWarp = kEpiWarps + 1;
 constexpr int kBuild0 = 32 * (kEpiWarps + 2);                  // first builder thread
 constexpr int kMma2Warp = kEpiWarps + 2 + kBuildWarps;         // second MMA issuer (the pass's second M tile)
 constexpr int kThreads = 32 * (kMma2Warp + 1);                 // 480
-#ifndef UMMA_SLOTS
-#define UMMA_SLOTS 4
-#endif
-constexpr int kSlots = UMMA_SLOTS;                             // operand ring
 constexpr int kTPP = 2;                                        // M tiles per pass
 constexpr uint32_t kTileBytes = 8192;                          // one 128 x 16 fp32 operand tile: [4 chunks][16 groups][8 rows][16 B]
 constexpr uint32_t kChunkBytes = 2048;                         // LBO of the A tiles (core matrices adjacent in K)
@@ -59,11 +64,6 @@ struct ConvUArgs {
 
 // ReLU as torch evaluates it: a NaN stays a NaN (fmaxf would return 0)
 __device__ __forceinline__ float relu_keep_nan(float v) { return v < 0.0f ? 0.0f : v; }
-__device__ __forceinline__ uint32_t tf32_rna(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
-}
 // shared-memory matrix descriptor, K-major, no swizzle: start address, LBO (K direction), SBO (M / N direction), version 1
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
