@@ -73,17 +73,6 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     d |= (uint64_t)1 << 46;
     return d;
 }
-// the same for the 64-byte swizzle (rows of 64 bytes = 16 values of K, 8-row atoms of 512 bytes; what a TMA box with
-// CU_TENSOR_MAP_SWIZZLE_64B writes): LBO is not used (1), SBO = 512, layout type 4 in bits 61-63
-__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
-    return d;
-}
 // instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -92,6 +81,19 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uin
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
                  "r"(accumulate)
+                 : "memory");
+}
+// the same with the A operand in tensor memory (lane = row, one 32-bit column per value of K)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc),
+                 "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+                 "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
                  : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -140,19 +142,25 @@ struct Shape {
     static constexpr int S = CIN == 5 ? 3 : 9 * G;                     // stages per pass (first layer: K = 45 -> 48)
     static constexpr uint32_t B_LBO = 32u * COUT;                      // (2 COUT / 8) row groups x 128 B
     static constexpr uint32_t B_BYTES = 4 * B_LBO;
-    // first layer: one ring of NH slots [hi 0 | lo 0 | hi 1 | lo 1 | B]; layers 2 / 3: a deep ring of TMA landing slots
-    // [hi 0 | hi 1 | B] and a short ring of lo slots [lo 0 | lo 1] that live only between the builders and the MMAs
-    static constexpr bool SPLIT = CIN != 5;
-    static constexpr uint32_t HT = SPLIT ? kTileBytes : 2 * kTileBytes;     // hi tile t at t * HT inside its slot
+    // first layer (SS form): one ring of NH slots [hi 0 | lo 0 | hi 1 | lo 1 | B] in shared memory, D = 2 COUT columns per tile
+    // layers 2 / 3 (TS form): a ring of TMA landing slots [hi 0 | hi 1 | B] in shared memory; the builders move the A
+    // operand -- hi as it is, lo computed -- into a short ring in TENSOR memory (64 columns per slot: per tile 16 hi + 16 lo,
+    // one 32-bit column per value of K) and the MMAs take A from there: the MMAs then read only the weights from shared
+    // memory (6 KB per tile and k-step instead of 14), nothing writes lo tiles, and D = COUT columns per tile with three
+    // MMAs per k-step (hi x B_hi, hi x B_lo, lo x B_hi; same tensor time as the two-MMA form)
+    static constexpr bool TS = CIN != 5;
+    static constexpr uint32_t HT = TS ? kTileBytes : 2 * kTileBytes;        // hi tile t at t * HT inside its slot
     static constexpr uint32_t BOFF = kTPP * HT;                              // weights behind the tiles
     static constexpr uint32_t SLOT = BOFF + B_BYTES;
-    static constexpr uint32_t LSLOT = kTPP * kTileBytes;
-    static constexpr int NH = !SPLIT ? 4 : (COUT <= 64 ? 6 : 5);
-    static constexpr int NL = !SPLIT ? 0 : (COUT <= 64 ? 3 : 2);
-    static constexpr int NBUF = 8 * COUT <= 512 ? 2 : 1;               // accumulator buffers in TMEM
-    static constexpr int TCOLS = 2 * COUT * kTPP;                      // columns per buffer
+    static constexpr int NH = !TS ? 4 : (COUT <= 64 ? 8 : 6);
+    static constexpr int NL = !TS ? 0 : (COUT <= 64 ? 3 : 2);               // A-operand slots in tensor memory
+    static constexpr int ACOLS = 64;                                        // columns per A slot
+    static constexpr int DCOLS = TS ? COUT : 2 * COUT;                      // accumulator columns per tile
+    static constexpr int TCOLS = DCOLS * kTPP;                              // ... per buffer
+    static constexpr int NBUF = (512 - NL * ACOLS) / TCOLS >= 2 ? 2 : 1;    // accumulator buffers
+    static constexpr int ABASE = NBUF * TCOLS;                              // first column of the A ring
     static constexpr uint32_t OUT_BYTES = POOL ? 0u : 2u * 16384u;                 // two staging buffers of 32 channels x 128 pixels for the TMA stores
-    static constexpr size_t SMEM = (size_t)NH * SLOT + (size_t)NL * LSLOT + OUT_BYTES + 512 /* barriers */ + COUT * 4 + (POOL ? 4 * 128 * 4 : 0) + 1024 /* alignment */;
+    static constexpr size_t SMEM = (size_t)NH * SLOT + OUT_BYTES + 512 /* barriers */ + COUT * 4 + (POOL ? 4 * 128 * 4 : 0) + 1024 /* alignment */;
 };
 
 template <int CIN, int COUT, bool POOL>
@@ -166,8 +174,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* basep = umma_smem_raw + (base - raw);
     constexpr int NH = Sh::NH, NL = Sh::NL > 0 ? Sh::NL : 1;
-    const uint32_t lobase = base + NH * Sh::SLOT;                      // lo ring (layers 2 / 3)
-    const uint32_t ostage = lobase + Sh::NL * Sh::LSLOT;               // 2 x [128 rows][128 B], 128-byte swizzle (store epilogue)
+    const uint32_t ostage = base + NH * Sh::SLOT;                      // 2 x [128 rows][128 B], 128-byte swizzle (store epilogue)
     const uint32_t bars = ostage + Sh::OUT_BYTES;                      // full[4] empty[4] tfull[2] tempty[2] | tmem holder | lofull[4]
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };      // 8 barriers each: full, empty, lofull, loempty, tfull | tempty (4 + 4)
@@ -212,6 +219,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const int row = tid;                                           // row of the M tile = TMEM lane
         const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
         uint32_t pc = 0, unit = 0;
+        // 16 accumulator columns of this thread's row (SS form: the hi*hi + lo*hi and the hi*lo halves added)
+        auto acc16 = [&](float (&p)[16], uint32_t col) {
+            tmem_ld16(p, col);
+            if constexpr (!Sh::TS) {
+                float q[16];
+                tmem_ld16(q, col + COUT);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) p[j] += q[j];
+            } else {
+                tmem_ld_wait();
+            }
+        };
         for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
             const int buf = (int)(pc % Sh::NBUF);
             const long long n = pass / half_tiles;
@@ -220,7 +240,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             tc_fence_after();
 #pragma unroll 1
             for (int t = 0; t < kTPP; ++t) {
-                const uint32_t tcol = lane_addr + (uint32_t)(buf * Sh::TCOLS + t * 2 * COUT);
+                const uint32_t tcol = lane_addr + (uint32_t)(buf * Sh::TCOLS + t * Sh::DCOLS);
                 if constexpr (!POOL) {
                     // the tile's output is 128 x COUT contiguous floats: staged in shared memory (row = pixel, 128-byte rows of
                     // 32 channels, 16-byte chunks XOR-swizzled with the row so the per-row stores are conflict free) and written by
@@ -236,17 +256,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                         asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
                         for (int j0 = 0; j0 < 32; j0 += 16) {
-                            float p[16], q[16];
-                            tmem_ld16(p, tcol + 32 * h + j0);
-                            tmem_ld16(q, tcol + COUT + 32 * h + j0);
-                            tmem_ld_wait();
+                            float p[16];
+                            acc16(p, tcol + 32 * h + j0);
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
                                 const int c = 32 * h + j0 + j;                           // first channel of this 16-byte chunk
-                                const uint32_t o0 = __float_as_uint(relu_keep_nan(p[j] + q[j] + bias_s[c]));
-                                const uint32_t o1 = __float_as_uint(relu_keep_nan(p[j + 1] + q[j + 1] + bias_s[c + 1]));
-                                const uint32_t o2 = __float_as_uint(relu_keep_nan(p[j + 2] + q[j + 2] + bias_s[c + 2]));
-                                const uint32_t o3 = __float_as_uint(relu_keep_nan(p[j + 3] + q[j + 3] + bias_s[c + 3]));
+                                const uint32_t o0 = __float_as_uint(relu_keep_nan(p[j] + bias_s[c]));
+                                const uint32_t o1 = __float_as_uint(relu_keep_nan(p[j + 1] + bias_s[c + 1]));
+                                const uint32_t o2 = __float_as_uint(relu_keep_nan(p[j + 2] + bias_s[c + 2]));
+                                const uint32_t o3 = __float_as_uint(relu_keep_nan(p[j + 3] + bias_s[c + 3]));
                                 const uint32_t addr = obuf + (uint32_t)row * 128u + ((((uint32_t)((j0 + j) >> 2)) ^ ((uint32_t)row & 7u)) << 4);
                                 if (!(UMMA_DBG & 8)) st_shared_v4(addr, o0, o1, o2, o3);
                             }
@@ -266,17 +284,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     for (int j0 = 0; j0 < COUT; j0 += 32) {
                         float v[32];
                         {
-                            float p[16], q[16];
-                            tmem_ld16(p, tcol + j0);
-                            tmem_ld16(q, tcol + COUT + j0);
-                            tmem_ld_wait();
+                            float p[16];
+                            acc16(p, tcol + j0);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = relu_keep_nan(p[j] + q[j] + bias_s[j0 + j]);
-                            tmem_ld16(p, tcol + j0 + 16);
-                            tmem_ld16(q, tcol + COUT + j0 + 16);
-                            tmem_ld_wait();
+                            for (int j = 0; j < 16; ++j) v[j] = relu_keep_nan(p[j] + bias_s[j0 + j]);
+                            acc16(p, tcol + j0 + 16);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) v[16 + j] = relu_keep_nan(p[j] + q[j] + bias_s[j0 + 16 + j]);
+                            for (int j = 0; j < 16; ++j) v[16 + j] = relu_keep_nan(p[j] + bias_s[j0 + 16 + j]);
                         }
                         rs_stage<16>(v, lane);
                         rs_stage<8>(v, lane);
@@ -310,34 +324,45 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         if (lane == 0) {
             const int t = warp == kMmaWarp ? 0 : 1;
             constexpr uint32_t idesc_cat = idesc_tf32(2 * COUT), idesc_one = idesc_tf32(COUT);
-            constexpr uint64_t kJA = TMA ? (32 >> 4) : ((2 * kChunkBytes) >> 4);              // second k-step of a stage, A
+            constexpr uint64_t kJA = (2 * kChunkBytes) >> 4;                                   // second k-step of a stage, A (SS form)
             constexpr uint64_t kJB = (2 * Sh::B_LBO) >> 4;                                      // ... and B
-            const uint64_t a0 = (TMA ? smem_desc_sw64(base) : smem_desc(base, kChunkBytes, 128)) + (uint64_t)((t * Sh::HT) >> 4);
-            const uint64_t l0 = TMA ? smem_desc_sw64(lobase) + (uint64_t)((t * kTileBytes) >> 4) : a0 + (kTileBytes >> 4);
+            constexpr uint64_t kBlo = (16u * COUT) >> 4;                                        // rows COUT.. of the weight image: the lo part
+            const uint64_t a0 = smem_desc(base, kChunkBytes, 128) + (uint64_t)((t * Sh::HT) >> 4);
             const uint64_t b0 = smem_desc(base + Sh::BOFF, Sh::B_LBO, 128);
             uint32_t it = 0, pc = 0;
             for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
                 const int buf = (int)(pc % Sh::NBUF);
                 mbar_wait(tempty_bar(buf), ((pc / Sh::NBUF) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t dcol = tm + (uint32_t)(buf * Sh::TCOLS + t * 2 * COUT);
+                const uint32_t dcol = tm + (uint32_t)(buf * Sh::TCOLS + t * Sh::DCOLS);
 #pragma unroll 1
                 for (int s = 0; s < S; ++s, ++it) {
                     const int slot = (int)(it % NH), ls = (int)(it % NL);
                     mbar_wait(full_bar(slot), (it / NH) & 1u);
-                    if constexpr (TMA) mbar_wait(lofull_bar(ls), (it / NL) & 1u);
+                    if constexpr (Sh::TS) mbar_wait(lofull_bar(ls), (it / NL) & 1u);
                     tc_fence_after();
                     const uint64_t so = (uint64_t)((slot * Sh::SLOT) >> 4);
-                    const uint64_t ahi = a0 + so, bd = b0 + so;
-                    const uint64_t alo = TMA ? l0 + (uint64_t)((ls * Sh::LSLOT) >> 4) : l0 + so;
+                    const uint64_t bd = b0 + so;
                     if (!(UMMA_DBG & 1)) {
-                        mma_tf32_ss(dcol, ahi, bd, idesc_cat, s != 0);
-                        mma_tf32_ss(dcol, alo, bd, idesc_one, 1u);
-                        mma_tf32_ss(dcol, ahi + kJA, bd + kJB, idesc_cat, 1u);
-                        mma_tf32_ss(dcol, alo + kJA, bd + kJB, idesc_one, 1u);
+                        if constexpr (Sh::TS) {
+                            // A from tensor memory: columns [hi 16 | lo 16] of this tile in slot ls, 8 per k-step
+                            const uint32_t ac = tm + (uint32_t)(Sh::ABASE + ls * Sh::ACOLS + t * 32);
+                            mma_tf32_ts(dcol, ac, bd, idesc_one, s != 0);
+                            mma_tf32_ts(dcol, ac, bd + kBlo, idesc_one, 1u);
+                            mma_tf32_ts(dcol, ac + 16, bd, idesc_one, 1u);
+                            mma_tf32_ts(dcol, ac + 8, bd + kJB, idesc_one, 1u);
+                            mma_tf32_ts(dcol, ac + 8, bd + kJB + kBlo, idesc_one, 1u);
+                            mma_tf32_ts(dcol, ac + 24, bd + kJB, idesc_one, 1u);
+                        } else {
+                            const uint64_t ahi = a0 + so, alo = ahi + (kTileBytes >> 4);
+                            mma_tf32_ss(dcol, ahi, bd, idesc_cat, s != 0);
+                            mma_tf32_ss(dcol, alo, bd, idesc_one, 1u);
+                            mma_tf32_ss(dcol, ahi + kJA, bd + kJB, idesc_cat, 1u);
+                            mma_tf32_ss(dcol, alo + kJA, bd + kJB, idesc_one, 1u);
+                        }
                     }
                     mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot
-                    if constexpr (TMA) mma_commit(loempty_bar(ls));
+                    if constexpr (Sh::TS) mma_commit(loempty_bar(ls));
                 }
                 mma_commit(tfull_bar(buf));                            // ... and once the accumulators are final
             }
@@ -373,33 +398,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             }
         }
     } else if constexpr (TMA) {
-        // ------------------------------------------------------------------------------------------ lo builders (layers 2 / 3)
-        // hi = x with the low 13 mantissa bits cleared is what the MMA makes of the raw tile; lo = x - hi is exact in fp32
-        // and is rounded to TF32 here (ties away, two integer instructions).  The lo tile mirrors the hi tile byte for byte,
-        // so the 64-byte swizzle never has to be spelled out.
-        const int bt = tid - kBuild0;
+        // ------------------------------------------------------------------------------------------ A-operand builders (layers 2 / 3)
+        // A thread owns one row (output pixel) of one M tile: warp % 4 is the TMEM lane quadrant it may write, the first four
+        // builder warps take tile 0, the other four tile 1.  Per stage it reads its 64-byte row of the landed (64-byte
+        // swizzled) tile -- chunk c at position c ^ ((row >> 1) & 3): conflict free over a quarter-warp -- and writes 16 hi
+        // and 16 lo values to tensor memory.  hi = x as it is (the MMA truncates it to TF32); lo = x - trunc(x) is exact in
+        // fp32 and is rounded to TF32 here (ties away, two integer instructions).
+        const int q = warp & 3, t = (warp - kBuild0 / 32) >> 2;
+        const int r = 32 * q + lane;
+        const uint32_t rowoff = (uint32_t)t * kTileBytes + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
+        const uint32_t tdst = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(Sh::ABASE + t * 32);
         const long long my_passes = (a.passes - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
         const long long total = my_passes * S;
         uint32_t it = 0;
-        for (long long q = 0; q < total; ++q, ++it) {
+        for (long long qq = 0; qq < total; ++qq, ++it) {
             const int slot = (int)(it % NH), ls = (int)(it % NL);
-            const uint32_t sa = base + slot * Sh::SLOT, sl = lobase + ls * Sh::LSLOT;
+            const uint32_t sa = base + slot * Sh::SLOT + rowoff;
             mbar_wait_relaxed(full_bar(slot), (it / NH) & 1u);
             mbar_wait_relaxed(loempty_bar(ls), ((it / NL) & 1u) ^ 1u);
+            tc_fence_after();
             if (!(UMMA_DBG & 2)) {
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i = 0; i < (int)(kTPP * kTileBytes / 16 / kBuildThreads); ++i) {
-                    const uint32_t off = ((uint32_t)bt + (uint32_t)i * kBuildThreads) * 16u;     // the two hi tiles are contiguous, so are the lo tiles
-                    uint32_t x0, x1, x2, x3;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sa + off));
-                    auto lo = [](uint32_t x) {
-                        const float l = __uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u);
-                        return (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
-                    };
-                    st_shared_v4(sl + off, lo(x0), lo(x1), lo(x2), lo(x3));
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(hi[4 * c]), "=r"(hi[4 * c + 1]), "=r"(hi[4 * c + 2]), "=r"(hi[4 * c + 3])
+                                 : "r"(sa + (((uint32_t)c ^ sw) << 4)));
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float l = __uint_as_float(hi[k]) - __uint_as_float(hi[k] & 0xFFFFE000u);
+                    lo[k] = (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
                 }
+                tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS), hi);
+                tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS) + 16, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
+            tc_fence_before();
             mbar_arrive(lofull_bar(ls));
         }
     } else {
