@@ -142,25 +142,27 @@ struct Shape {
     static constexpr int S = CIN == 5 ? 3 : 9 * G;                     // stages per pass (first layer: K = 45 -> 48)
     static constexpr uint32_t B_LBO = 32u * COUT;                      // (2 COUT / 8) row groups x 128 B
     static constexpr uint32_t B_BYTES = 4 * B_LBO;
-    // first layer (SS form): one ring of NH slots [hi 0 | lo 0 | hi 1 | lo 1 | B] in shared memory, D = 2 COUT columns per tile
-    // layers 2 / 3 (TS form): a ring of TMA landing slots [hi 0 | hi 1 | B] in shared memory; the builders move the A
-    // operand -- hi as it is, lo computed -- into a short ring in TENSOR memory (64 columns per slot: per tile 16 hi + 16 lo,
-    // one 32-bit column per value of K) and the MMAs take A from there: the MMAs then read only the weights from shared
-    // memory (6 KB per tile and k-step instead of 14), nothing writes lo tiles, and D = COUT columns per tile with three
-    // MMAs per k-step (hi x B_hi, hi x B_lo, lo x B_hi; same tensor time as the two-MMA form)
-    static constexpr bool TS = CIN != 5;
-    static constexpr uint32_t HT = TS ? kTileBytes : 2 * kTileBytes;        // hi tile t at t * HT inside its slot
-    static constexpr uint32_t BOFF = kTPP * HT;                              // weights behind the tiles
+    // TS form: the A operand lives in TENSOR memory, a short ring of NL slots of 64 columns (per M tile 16 hi + 16 lo
+    // columns, one 32-bit column per value of K) written by the builder warps; the MMAs read only the weights from shared
+    // memory.  Layers 2 / 3: a ring of TMA landing slots [hi 0 | hi 1 | B] in shared memory feeds the builders; first
+    // layer: the builders gather from global memory and a slot holds the stage's weights only.
+    // CAT (two-MMA form, D = 2 COUT columns per tile: hi x [B_hi ; B_lo], lo x B_hi) where tensor memory has the room,
+    // otherwise three MMAs of N = COUT per k-step (hi x B_hi, hi x B_lo, lo x B_hi) into COUT columns.
+    static constexpr bool GATHER = CIN == 5;
+    static constexpr uint32_t BOFF = GATHER ? 0u : kTPP * kTileBytes;       // weights behind the tiles
     static constexpr uint32_t SLOT = BOFF + B_BYTES;
-    static constexpr int NH = !TS ? 4 : (COUT <= 64 ? 8 : 6);
-    static constexpr int NL = !TS ? 0 : (COUT <= 64 ? 3 : 2);               // A-operand slots in tensor memory
+    static constexpr int NH = GATHER ? 8 : (COUT <= 64 ? 8 : 6);
+    static constexpr int NL = GATHER ? 4 : (COUT <= 64 ? 3 : 2);            // A-operand slots in tensor memory
     static constexpr int ACOLS = 64;                                        // columns per A slot
-    static constexpr int DCOLS = TS ? COUT : 2 * COUT;                      // accumulator columns per tile
+    static constexpr bool CAT = GATHER;
+    static constexpr int DCOLS = CAT ? 2 * COUT : COUT;                     // accumulator columns per tile
     static constexpr int TCOLS = DCOLS * kTPP;                              // ... per buffer
     static constexpr int NBUF = (512 - NL * ACOLS) / TCOLS >= 2 ? 2 : 1;    // accumulator buffers
     static constexpr int ABASE = NBUF * TCOLS;                              // first column of the A ring
+    static constexpr uint32_t RAW_SLOT = GATHER ? 26u * 1024u : 0u;         // first layer: the input rows of one pass (W <= 256: 5 bands x 5 rows)
+    static constexpr int NR = GATHER ? 5 : 0;                               // ... and how many passes are in flight
     static constexpr uint32_t OUT_BYTES = POOL ? 0u : 2u * 16384u;                 // two staging buffers of 32 channels x 128 pixels for the TMA stores
-    static constexpr size_t SMEM = (size_t)NH * SLOT + OUT_BYTES + 512 /* barriers */ + COUT * 4 + (POOL ? 4 * 128 * 4 : 0) + 1024 /* alignment */;
+    static constexpr size_t SMEM = (size_t)NH * SLOT + (size_t)NR * RAW_SLOT + OUT_BYTES + 512 /* barriers */ + COUT * 4 + (POOL ? 4 * 128 * 4 : 0) + 1024 /* alignment */;
 };
 
 template <int CIN, int COUT, bool POOL>
@@ -174,7 +176,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* basep = umma_smem_raw + (base - raw);
     constexpr int NH = Sh::NH, NL = Sh::NL > 0 ? Sh::NL : 1;
-    const uint32_t ostage = base + NH * Sh::SLOT;                      // 2 x [128 rows][128 B], 128-byte swizzle (store epilogue)
+    const uint32_t rawbase = base + NH * Sh::SLOT;                     // first layer: ring of staged input rows
+    const uint32_t ostage = rawbase + Sh::NR * Sh::RAW_SLOT;           // 2 x [128 rows][128 B], 128-byte swizzle (store epilogue)
     const uint32_t bars = ostage + Sh::OUT_BYTES;                      // full[4] empty[4] tfull[2] tempty[2] | tmem holder | lofull[4]
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 64u + 8u * s; };      // 8 barriers each: full, empty, lofull, loempty, tfull | tempty (4 + 4)
@@ -182,6 +185,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     auto loempty_bar = [&](int s) { return bars + 192u + 8u * s; };
     auto tfull_bar = [&](int b) { return bars + 256u + 8u * b; };
     auto tempty_bar = [&](int b) { return bars + 288u + 8u * b; };
+    auto rawfull_bar = [&](int s) { return bars + 352u + 8u * s; };
+    auto rawempty_bar = [&](int s) { return bars + 416u + 8u * s; };
     volatile uint32_t* tmem_holder = reinterpret_cast<volatile uint32_t*>(basep + (ostage - base) + Sh::OUT_BYTES + 320);
     float* bias_s = reinterpret_cast<float*>(basep + (ostage - base) + Sh::OUT_BYTES + 512);
     float* red_s = bias_s + COUT;                                      // [4 warps][128] (pooling only)
@@ -189,13 +194,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < NH; ++s) {
-            // first layer: the slot's builder group after its stores + the weight copy's expect_tx; others: the producer's expect_tx
-            mbar_init(full_bar(s), TMA ? 1 : kBuildThreads / NH + 1);
+            mbar_init(full_bar(s), 1);                                 // the producer's expect_tx
             mbar_init(empty_bar(s), kTPP);                             // one tcgen05.commit per MMA issuer
         }
         for (int s = 0; s < NL; ++s) {
             mbar_init(lofull_bar(s), kBuildThreads);                   // every builder after its lo stores
             mbar_init(loempty_bar(s), kTPP);
+        }
+        for (int s = 0; s < Sh::NR; ++s) {
+            mbar_init(rawfull_bar(s), 1);
+            mbar_init(rawempty_bar(s), kBuildThreads);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), kTPP);
@@ -213,6 +221,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     tc_fence_after();
     const uint32_t tm = *tmem_holder;
     const int half_tiles = a.tiles / kTPP;
+    // a CTA takes a contiguous run of passes: consecutive passes are neighbouring rows of one patch, so the rows two tiles
+    // share and the taps' re-reads stay hot in L2 (a grid-strided assignment jumped 2.3 patches per pass: the first-layer
+    // gather waited a third of its time on DRAM / TLB misses)
+    const long long p_begin = a.passes * (long long)blockIdx.x / gridDim.x, p_end = a.passes * (long long)(blockIdx.x + 1) / gridDim.x;
 
     if (warp < kEpiWarps) {
         // ------------------------------------------------------------------------------------------ epilogue
@@ -222,7 +234,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // 16 accumulator columns of this thread's row (SS form: the hi*hi + lo*hi and the hi*lo halves added)
         auto acc16 = [&](float (&p)[16], uint32_t col) {
             tmem_ld16(p, col);
-            if constexpr (!Sh::TS) {
+            if constexpr (Sh::CAT) {
                 float q[16];
                 tmem_ld16(q, col + COUT);
                 tmem_ld_wait();
@@ -232,7 +244,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 tmem_ld_wait();
             }
         };
-        for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
+        for (long long pass = p_begin; pass < p_end; ++pass, ++pc) {
             const int buf = (int)(pc % Sh::NBUF);
             const long long n = pass / half_tiles;
             const int tile0 = (int)(pass - n * half_tiles) * kTPP;
@@ -324,13 +336,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         if (lane == 0) {
             const int t = warp == kMmaWarp ? 0 : 1;
             constexpr uint32_t idesc_cat = idesc_tf32(2 * COUT), idesc_one = idesc_tf32(COUT);
-            constexpr uint64_t kJA = (2 * kChunkBytes) >> 4;                                   // second k-step of a stage, A (SS form)
-            constexpr uint64_t kJB = (2 * Sh::B_LBO) >> 4;                                      // ... and B
+            constexpr uint64_t kJB = (2 * Sh::B_LBO) >> 4;                                      // second k-step of a stage, B
             constexpr uint64_t kBlo = (16u * COUT) >> 4;                                        // rows COUT.. of the weight image: the lo part
-            const uint64_t a0 = smem_desc(base, kChunkBytes, 128) + (uint64_t)((t * Sh::HT) >> 4);
             const uint64_t b0 = smem_desc(base + Sh::BOFF, Sh::B_LBO, 128);
             uint32_t it = 0, pc = 0;
-            for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x, ++pc) {
+            for (long long pass = p_begin; pass < p_end; ++pass, ++pc) {
                 const int buf = (int)(pc % Sh::NBUF);
                 mbar_wait(tempty_bar(buf), ((pc / Sh::NBUF) & 1u) ^ 1u);
                 tc_fence_after();
@@ -339,43 +349,72 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 for (int s = 0; s < S; ++s, ++it) {
                     const int slot = (int)(it % NH), ls = (int)(it % NL);
                     mbar_wait(full_bar(slot), (it / NH) & 1u);
-                    if constexpr (Sh::TS) mbar_wait(lofull_bar(ls), (it / NL) & 1u);
+                    mbar_wait(lofull_bar(ls), (it / NL) & 1u);
                     tc_fence_after();
-                    const uint64_t so = (uint64_t)((slot * Sh::SLOT) >> 4);
-                    const uint64_t bd = b0 + so;
+                    const uint64_t bd = b0 + (uint64_t)((slot * Sh::SLOT) >> 4);
                     if (!(UMMA_DBG & 1)) {
-                        if constexpr (Sh::TS) {
-                            // A from tensor memory: columns [hi 16 | lo 16] of this tile in slot ls, 8 per k-step
-                            const uint32_t ac = tm + (uint32_t)(Sh::ABASE + ls * Sh::ACOLS + t * 32);
+                        // A from tensor memory: columns [hi 16 | lo 16] of this tile in slot ls, 8 per k-step
+                        const uint32_t ac = tm + (uint32_t)(Sh::ABASE + ls * Sh::ACOLS + t * 32);
+                        if constexpr (Sh::CAT) {
+                            mma_tf32_ts(dcol, ac, bd, idesc_cat, s != 0);
+                            mma_tf32_ts(dcol, ac + 16, bd, idesc_one, 1u);
+                            mma_tf32_ts(dcol, ac + 8, bd + kJB, idesc_cat, 1u);
+                            mma_tf32_ts(dcol, ac + 24, bd + kJB, idesc_one, 1u);
+                        } else {
                             mma_tf32_ts(dcol, ac, bd, idesc_one, s != 0);
                             mma_tf32_ts(dcol, ac, bd + kBlo, idesc_one, 1u);
                             mma_tf32_ts(dcol, ac + 16, bd, idesc_one, 1u);
                             mma_tf32_ts(dcol, ac + 8, bd + kJB, idesc_one, 1u);
                             mma_tf32_ts(dcol, ac + 8, bd + kJB + kBlo, idesc_one, 1u);
                             mma_tf32_ts(dcol, ac + 24, bd + kJB, idesc_one, 1u);
-                        } else {
-                            const uint64_t ahi = a0 + so, alo = ahi + (kTileBytes >> 4);
-                            mma_tf32_ss(dcol, ahi, bd, idesc_cat, s != 0);
-                            mma_tf32_ss(dcol, alo, bd, idesc_one, 1u);
-                            mma_tf32_ss(dcol, ahi + kJA, bd + kJB, idesc_cat, 1u);
-                            mma_tf32_ss(dcol, alo + kJA, bd + kJB, idesc_one, 1u);
                         }
                     }
-                    mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot
-                    if constexpr (Sh::TS) mma_commit(loempty_bar(ls));
+                    mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot's weights
+                    mma_commit(loempty_bar(ls));                       // ... and the A slot
                 }
                 mma_commit(tfull_bar(buf));                            // ... and once the accumulators are final
             }
         }
     } else if (warp == kTmaWarp) {
         // ------------------------------------------------------------------------------------------ TMA producer (layers 2 / 3)
-        if constexpr (TMA) {
+        if constexpr (!TMA) {
+            // first layer: lane 0 fetches the input rows of a pass (all 5 bands, the 4 (128 / Wo) + 1 rows its two tiles touch,
+            // full width; rows above the image are zero-filled = the padding) as one TMA box per pass, Sh::NR passes ahead of
+            // the gather; lane 2 streams the weight stages
+            if (lane == 0) {
+                const int rpt = 128 / a.Wo;
+                const uint32_t bytes = (uint32_t)(a.W * (4 * rpt + 1) * CIN * 4);
+                uint32_t pc = 0;
+                for (long long pass = p_begin; pass < p_end; ++pass, ++pc) {
+                    const long long n = pass / half_tiles;
+                    const int tile0 = (int)(pass - n * half_tiles) * kTPP;
+                    const int rs = (int)(pc % Sh::NR);
+                    mbar_wait(rawempty_bar(rs), ((pc / Sh::NR) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(rawfull_bar(rs), bytes);
+                    tma_load_4d(rawbase + rs * Sh::RAW_SLOT, &tmap, 0, 2 * tile0 * rpt - 1, 0, (int)n, rawfull_bar(rs));
+                }
+            } else if (lane == 2) {
+                uint32_t it = 0;
+                for (long long pass = p_begin; pass < p_end; ++pass) {
+#pragma unroll 1
+                    for (int s = 0; s < S; ++s, ++it) {
+                        const int slot = (int)(it % NH);
+                        mbar_wait(empty_bar(slot), ((it / NH) & 1u) ^ 1u);
+                        if (UMMA_DBG & 4) mbar_arrive(full_bar(slot));
+                        else {
+                            mbar_arrive_expect_tx(full_bar(slot), Sh::B_BYTES);
+                            bulk_g2s(base + slot * Sh::SLOT + Sh::BOFF, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
+                        }
+                    }
+                }
+            }
+        } else {
             // three lanes, one request each per stage (a single thread sustains about one TMA request per 280 ns):
             // lanes 0 / 1 the two M tiles' boxes, lane 2 the weight stage; lane 0 also posts the byte count
             if (lane < kTPP + 1) {
                 const int rows_per_tile = 128 / a.Wo;                  // output rows of one M tile
                 uint32_t it = 0;
-                for (long long pass = blockIdx.x; pass < a.passes; pass += gridDim.x) {
+                for (long long pass = p_begin; pass < p_end; ++pass) {
                     const long long n = pass / half_tiles;
                     const int tile0 = (int)(pass - n * half_tiles) * kTPP;
 #pragma unroll 1
@@ -408,7 +447,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const int r = 32 * q + lane;
         const uint32_t rowoff = (uint32_t)t * kTileBytes + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
         const uint32_t tdst = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(Sh::ABASE + t * 32);
-        const long long my_passes = (a.passes - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const long long my_passes = p_end - p_begin;
         const long long total = my_passes * S;
         uint32_t it = 0;
         for (long long qq = 0; qq < total; ++qq, ++it) {
@@ -437,117 +476,73 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             mbar_arrive(lofull_bar(ls));
         }
     } else {
-        // ------------------------------------------------------------------------------------------ operand builders (first layer)
-        // The 5-band [N, 5, H, W] input cannot be fetched as K-major TMA boxes (a 16-byte chunk of the operand is four taps of
-        // one pixel), so threads gather it.  Four groups of two warps; group g owns ring slot g and builds every fourth stage
-        // of the CTA's flat stage sequence.  A group's loads are issued right after it has published a stage and are consumed
-        // one group-iteration later, so the proxy fence of a stage (a MEMBAR: it waits for every load the thread has in
-        // flight) never sees a prefetch; the load latency is hidden by the other three groups instead.
+        // ------------------------------------------------------------------------------------------ A-operand builders (first layer)
+        // The 5-band [N, 5, H, W] input cannot be fetched as K-major boxes (a 16-byte chunk of the operand would be four taps
+        // of one pixel), so threads gather it -- from the input rows the producer staged in shared memory (a gather from
+        // global memory waited a third of its time on load latency even with the loads issued a pass ahead) straight into
+        // tensor memory: a thread owns one row (output pixel) of one M tile (warp % 4 = TMEM lane quadrant, first four
+        // builder warps tile 0, the others tile 1) and writes 16 hi and 16 lo values per stage with two tcgen05.st.
         // K order: stage s holds the five (band, row) triples T = 5 s + j, j < 5 (band = T / 3, dy = T % 3), k = 3 j + dx,
-        // k = 15 is zero.  A thread owns 4 pixels (R_i = 64 i + t64: a warp = 32 adjacent pixels of one output row); per triple
-        // it loads the aligned pair (2 ox, 2 ox + 1) -- one coalesced 256-byte request per warp -- and takes column 2 ox - 1
-        // from its left neighbour's pair by shuffle when the stage is stored (lane 0 loads it itself): a third of the
-        // load instructions of the scalar gather, which was bound by the L1 tag rate.
-        const int bt = tid - kBuild0, grp = bt >> 6, t64 = bt & 63;
-        const uint32_t sa = base + grp * Sh::SLOT;
-        const long long my_passes = (a.passes - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
-        float2 pr[4][5];
-        float ex[4][5];
-        int offs[4];                                                   // element offset of input pixel (2 oy - 1, 2 ox) in the patch
-        uint32_t edge = 0;                                             // bit 2 i: pixel i at oy == 0, bit 2 i + 1: ox == 0
-        const float* pbase = a.in;
-        long long cur = -1;
-        auto set_pass = [&](long long pl) {
-            cur = pl;
-            const long long pass = (long long)blockIdx.x + pl * gridDim.x;
-            const long long n = pass / half_tiles;
-            const int tile0 = (int)(pass - n * half_tiles) * kTPP;
-            pbase = a.in + (long long)n * CIN * a.H * a.W;
-            edge = 0;
+        // k = 15 is zero.  Per triple a lane reads the aligned pair (2 ox, 2 ox + 1) -- conflict free: a warp reads 256
+        // contiguous bytes -- and takes column 2 ox - 1 from its left neighbour's pair by shuffle (lane 0 reads it itself).
+        const int q = warp & 3, t = (warp - kBuild0 / 32) >> 2;
+        const int r = 32 * q + lane;
+        const uint32_t tdst = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(Sh::ABASE + t * 32);
+        const int RB = 4 * (128 / a.Wo) + 1;                            // staged rows per band
+        const int Pl = t * 128 + r, oyl = Pl / a.Wo, ox = Pl - oyl * a.Wo;       // this thread's pixel inside any pass
+        const uint32_t poff = (uint32_t)((2 * oyl * a.W + 2 * ox) * 4);          // staged row 2 oyl, column 2 ox of band 0
+        const bool left_ok = lane == 0 && ox != 0;
+        uint32_t it = 0, pc = 0;
+        for (long long pass = p_begin; pass < p_end; ++pass, ++pc) {
+            const int rs = (int)(pc % Sh::NR);
+            const uint32_t rawp = rawbase + rs * Sh::RAW_SLOT + poff;
+            mbar_wait_relaxed(rawfull_bar(rs), (pc / Sh::NR) & 1u);
+            float2 pr[3][5];
+            float ex[3][5];
+            if (!(UMMA_DBG & 2)) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int P = tile0 * 128 + 64 * i + t64;
-                const int oy = P / a.Wo, ox = P - oy * a.Wo;
-                offs[i] = (2 * oy - 1) * a.W + 2 * ox;
-                edge |= ((oy == 0 ? 1u : 0u) | (ox == 0 ? 2u : 0u)) << (2 * i);
+                for (int u = 0; u < 3; ++u)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const int T = 5 * u + j, ch = T / 3, dy = T - 3 * ch;
+                        const uint32_t ad = rawp + (uint32_t)(((ch * RB + dy) * a.W) * 4);
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(pr[u][j].x), "=f"(pr[u][j].y) : "r"(ad));
+                        ex[u][j] = 0.0f;
+                        if (left_ok) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ex[u][j]) : "r"(ad - 4));
+                    }
             }
-        };
-        const long long HW = (long long)a.H * a.W;
-        auto load_stage = [&](int s) {
+            // mbarrier.arrive does not wait for the thread's outstanding LDS (load-completion fence): a CTA-scope
+            // fence between the loads and the release of the slot
+            __threadfence_block();
+            mbar_arrive(rawempty_bar(rs));
 #pragma unroll
-            for (int sc = 0; sc < 3; ++sc)                             // the stage as a compile-time constant: (band, dy) of a triple fold
-                if (s == sc) {
+            for (int u = 0; u < 3; ++u, ++it) {
+                const int ls = (int)(it % NL);
+                uint32_t hi[16], lo[16];
+                if (!(UMMA_DBG & 2)) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const bool top = (edge >> (2 * i)) & 1u, left_ok = lane == 0 && !((edge >> (2 * i + 1)) & 1u);
-                        const float* p0 = pbase + offs[i];
+                    for (int j = 0; j < 5; ++j) {
+                        const float left = __shfl_up_sync(0xffffffffu, pr[u][j].y, 1);
+                        hi[3 * j] = __float_as_uint(lane == 0 ? ex[u][j] : left);
+                        hi[3 * j + 1] = __float_as_uint(pr[u][j].x);
+                        hi[3 * j + 2] = __float_as_uint(pr[u][j].y);
+                    }
+                    hi[15] = 0u;
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) {
-                            constexpr int kDummy = 0;
-                            (void)kDummy;
-                            const int T = 5 * sc + j, ch = T / 3, dy = T - 3 * ch;
-                            const bool row_ok = !(dy == 0 && top);
-                            const float* p = p0 + ch * HW + dy * a.W;
-                            pr[i][j] = row_ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.f, 0.f);
-                            ex[i][j] = (row_ok && left_ok) ? __ldg(p - 1) : 0.0f;
-                        }
+                    for (int k = 0; k < 16; ++k) {
+                        const float l = __uint_as_float(hi[k]) - __uint_as_float(hi[k] & 0xFFFFE000u);
+                        lo[k] = (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
                     }
                 }
-        };
-        // TF32 split: the hi tile holds x itself (the tensor core reads its upper 19 bits, i.e. truncates); lo = x minus the
-        // truncated x is exact in fp32 and is rounded to TF32 (ties away, two integer instructions).
-        // Where a chunk goes inside the slot: tile t, part (hi / lo), chunk c, row r -> (2 t + part) 8192 + 2048 c + 128 (r / 8) + 16 (r % 8)
-        auto store_stage = [&]() {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const float left = __shfl_up_sync(0xffffffffu, pr[i][j].y, 1);
-                    v[3 * j] = lane == 0 ? ex[i][j] : left;
-                    v[3 * j + 1] = pr[i][j].x;
-                    v[3 * j + 2] = pr[i][j].y;
+                mbar_wait_relaxed(loempty_bar(ls), ((it / NL) & 1u) ^ 1u);
+                tc_fence_after();
+                if (!(UMMA_DBG & 2)) {
+                    tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS), hi);
+                    tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS) + 16, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
-                v[15] = 0.0f;
-                const int R = 64 * i + t64;
-                const uint32_t d0 = sa + (uint32_t)((2 * (R >> 7)) * kTileBytes + ((R & 127) >> 3) * 128 + (R & 7) * 16);
-                auto lo = [](float x) {
-                    const float l = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                    return (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
-                };
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t d = d0 + c * kChunkBytes;
-                    st_shared_v4(d, __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]), __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
-                    st_shared_v4(d + kTileBytes, lo(v[4 * c]), lo(v[4 * c + 1]), lo(v[4 * c + 2]), lo(v[4 * c + 3]));
-                }
-            }
-        };
-        // flat stage sequence of this CTA: (local pass pl, stage s), this group takes every fourth
-        long long pl = 0;
-        int s = grp;
-        while (s >= S) { s -= S; ++pl; }
-        if (pl < my_passes && !(UMMA_DBG & 2)) {
-            set_pass(pl);
-            load_stage(s);
-        }
-        for (uint32_t m = 0; pl < my_passes; ++m) {
-            mbar_wait_relaxed(empty_bar(grp), (m & 1u) ^ 1u);
-            if (t64 == 0) {
-                if (UMMA_DBG & 4) mbar_arrive(full_bar(grp));
-                else {
-                    mbar_arrive_expect_tx(full_bar(grp), Sh::B_BYTES);
-                    bulk_g2s(sa + Sh::BOFF, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(grp));
-                }
-            }
-            if (!(UMMA_DBG & 2)) store_stage();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's reads
-            mbar_arrive(full_bar(grp));
-            s += NH;
-            while (s >= S) { s -= S; ++pl; }
-            if (pl < my_passes && !(UMMA_DBG & 2)) {
-                if (pl != cur) set_pass(pl);
-                load_stage(s);
+                tc_fence_before();
+                mbar_arrive(lofull_bar(ls));
             }
         }
     }
@@ -563,7 +558,20 @@ int launch_conv_umma(const ConvUArgs& a, long long N, int sms, cudaStream_t st) 
     KMSR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Sh::SMEM));
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    if (CIN != 5) {
+    if (CIN == 5) {
+        // [N, 5, H, W] seen as (x, y, band, n); one box = the rows of one pass: full width x 4 (128 / Wo) + 1 rows x 5 bands
+        EncodeTiledFn enc = get_tensor_map_encoder();
+        KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled is not available");
+        KMSR_REQUIRE(a.W <= 256 && (size_t)a.W * (4 * (128 / a.Wo) + 1) * 5 * 4 <= Sh::RAW_SLOT, KMSR_E_UNSUPPORTED,
+                     "selector (tcgen05): first-layer rows of %d pixels do not fit the staging slot", a.W);
+        cuuint64_t gdim[4] = {(cuuint64_t)a.W, (cuuint64_t)a.H, 5, (cuuint64_t)N};
+        cuuint64_t gstr[3] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.H * a.W * 4, (cuuint64_t)a.H * a.W * 20};
+        cuuint32_t box[4] = {(cuuint32_t)a.W, (cuuint32_t)(4 * (128 / a.Wo) + 1), 5, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)a.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled (input rows) failed with CUresult %d", (int)cr);
+    } else {
         // channel-last activations [N, H, W, CIN] seen as (c, x, y, n); one box = one 128-pixel M tile of one 16-channel
         // group of one tap: 16 channels x Wo pixels (every second column) x 128 / Wo rows (every second row), 64-byte swizzle
         EncodeTiledFn enc = get_tensor_map_encoder();
