@@ -139,7 +139,9 @@ __device__ __forceinline__ void rs_stage(float (&v)[32], int lane) {
 template <int CIN, int COUT, bool POOL>
 struct Shape {
     static constexpr int G = CIN >= 16 ? CIN / 16 : 1;                 // channel groups of 16 per tap
-    static constexpr int S = CIN == 5 ? 3 : 9 * G;                     // stages per pass (first layer: K = 45 -> 48)
+    static constexpr int SUB = CIN == 5 ? 1 : 2;                       // K = 16 sub-stages per stage: the issuing thread's per-stage cost
+                                                                       // (two barrier waits, two commits) is paid once per 12 MMAs, not per 6
+    static constexpr int S = CIN == 5 ? 3 : 9 * G / SUB;               // stages per pass (first layer: K = 45 -> 48)
     static constexpr uint32_t B_LBO = 32u * COUT;                      // (2 COUT / 8) row groups x 128 B
     static constexpr uint32_t B_BYTES = 4 * B_LBO;
     // TS form: the A operand lives in TENSOR memory, a short ring of NL slots of 64 columns (per M tile 16 hi + 16 lo
@@ -149,11 +151,11 @@ struct Shape {
     // CAT (two-MMA form, D = 2 COUT columns per tile: hi x [B_hi ; B_lo], lo x B_hi) where tensor memory has the room,
     // otherwise three MMAs of N = COUT per k-step (hi x B_hi, hi x B_lo, lo x B_hi) into COUT columns.
     static constexpr bool GATHER = CIN == 5;
-    static constexpr uint32_t BOFF = GATHER ? 0u : kTPP * kTileBytes;       // weights behind the tiles
-    static constexpr uint32_t SLOT = BOFF + B_BYTES;
-    static constexpr int NH = GATHER ? 8 : (COUT <= 64 ? 8 : 6);
-    static constexpr int NL = GATHER ? 4 : (COUT <= 64 ? 3 : 2);            // A-operand slots in tensor memory
-    static constexpr int ACOLS = 64;                                        // columns per A slot
+    static constexpr uint32_t BOFF = GATHER ? 0u : SUB * kTPP * kTileBytes; // weights behind the tiles [sub-stage][tile]
+    static constexpr uint32_t SLOT = BOFF + SUB * B_BYTES;
+    static constexpr int NH = GATHER ? 8 : (COUT <= 64 ? 4 : 3);
+    static constexpr int NL = GATHER ? 4 : 2;                               // A-operand slots in tensor memory
+    static constexpr int ACOLS = 64 * SUB;                                  // columns per A slot: [tile][sub-stage][hi 16 | lo 16]
     static constexpr bool CAT = GATHER;
     static constexpr int DCOLS = CAT ? 2 * COUT : COUT;                     // accumulator columns per tile
     static constexpr int TCOLS = DCOLS * kTPP;                              // ... per buffer
@@ -353,20 +355,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     tc_fence_after();
                     const uint64_t bd = b0 + (uint64_t)((slot * Sh::SLOT) >> 4);
                     if (!(UMMA_DBG & 1)) {
-                        // A from tensor memory: columns [hi 16 | lo 16] of this tile in slot ls, 8 per k-step
-                        const uint32_t ac = tm + (uint32_t)(Sh::ABASE + ls * Sh::ACOLS + t * 32);
-                        if constexpr (Sh::CAT) {
-                            mma_tf32_ts(dcol, ac, bd, idesc_cat, s != 0);
-                            mma_tf32_ts(dcol, ac + 16, bd, idesc_one, 1u);
-                            mma_tf32_ts(dcol, ac + 8, bd + kJB, idesc_cat, 1u);
-                            mma_tf32_ts(dcol, ac + 24, bd + kJB, idesc_one, 1u);
-                        } else {
-                            mma_tf32_ts(dcol, ac, bd, idesc_one, s != 0);
-                            mma_tf32_ts(dcol, ac, bd + kBlo, idesc_one, 1u);
-                            mma_tf32_ts(dcol, ac + 16, bd, idesc_one, 1u);
-                            mma_tf32_ts(dcol, ac + 8, bd + kJB, idesc_one, 1u);
-                            mma_tf32_ts(dcol, ac + 8, bd + kJB + kBlo, idesc_one, 1u);
-                            mma_tf32_ts(dcol, ac + 24, bd + kJB, idesc_one, 1u);
+                        // A from tensor memory: columns [hi 16 | lo 16] per sub-stage of this tile in slot ls, 8 per k-step
+#pragma unroll
+                        for (int h = 0; h < Sh::SUB; ++h) {
+                            const uint32_t ac = tm + (uint32_t)(Sh::ABASE + ls * Sh::ACOLS + t * 32 * Sh::SUB + h * 32);
+                            const uint64_t bh = bd + (uint64_t)((h * Sh::B_BYTES) >> 4);
+                            if constexpr (Sh::CAT) {
+                                mma_tf32_ts(dcol, ac, bh, idesc_cat, (s | h) != 0);
+                                mma_tf32_ts(dcol, ac + 16, bh, idesc_one, 1u);
+                                mma_tf32_ts(dcol, ac + 8, bh + kJB, idesc_cat, 1u);
+                                mma_tf32_ts(dcol, ac + 24, bh + kJB, idesc_one, 1u);
+                            } else {
+                                mma_tf32_ts(dcol, ac, bh, idesc_one, (s | h) != 0);
+                                mma_tf32_ts(dcol, ac, bh + kBlo, idesc_one, 1u);
+                                mma_tf32_ts(dcol, ac + 16, bh, idesc_one, 1u);
+                                mma_tf32_ts(dcol, ac + 8, bh + kJB, idesc_one, 1u);
+                                mma_tf32_ts(dcol, ac + 8, bh + kJB + kBlo, idesc_one, 1u);
+                                mma_tf32_ts(dcol, ac + 24, bh + kJB, idesc_one, 1u);
+                            }
                         }
                     }
                     mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot's weights
@@ -409,10 +415,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                 }
             }
         } else {
-            // three lanes, one request each per stage (a single thread sustains about one TMA request per 280 ns):
-            // lanes 0 / 1 the two M tiles' boxes, lane 2 the weight stage; lane 0 also posts the byte count
-            if (lane < kTPP + 1) {
+            // one lane per request of a stage (a single thread sustains about one TMA request per 280 ns): lanes
+            // 0 .. 3 the boxes (sub-stage, tile), lane 4 the weight stages; lane 0 also posts the byte count
+            constexpr int NBOX = Sh::SUB * kTPP, GS = G / Sh::SUB;
+            if (lane < NBOX + 1) {
                 const int rows_per_tile = 128 / a.Wo;                  // output rows of one M tile
+                const int bt = lane % kTPP, bh = lane / kTPP;          // this lane's box: tile, sub-stage
                 uint32_t it = 0;
                 for (long long pass = p_begin; pass < p_end; ++pass) {
                     const long long n = pass / half_tiles;
@@ -421,17 +429,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     for (int s = 0; s < S; ++s, ++it) {
                         const int slot = (int)(it % NH);
                         const uint32_t sa = base + slot * Sh::SLOT;
-                        const int tap = s / G, g = s - tap * G;
+                        const int tap = s / GS, g = (s - tap * GS) * Sh::SUB + bh;       // 16-channel group of this lane's box
                         const int dy = tap / 3, dx = tap - 3 * dy;
                         mbar_wait(empty_bar(slot), ((it / NH) & 1u) ^ 1u);
-                        if (lane == 0) mbar_arrive_expect_tx(full_bar(slot), kTPP * kTileBytes + ((UMMA_DBG & 4) ? 0u : Sh::B_BYTES));
+                        if (lane == 0)
+                            mbar_arrive_expect_tx(full_bar(slot), NBOX * kTileBytes + ((UMMA_DBG & 4) ? 0u : Sh::SUB * Sh::B_BYTES));
                         // the raw fp32 activations ARE the hi operand (the tensor core reads the upper 19 bits): box = 16 channels
                         // x Wo pixels at stride 2 x (128 / Wo) rows at stride 2, zero-filled outside the image = the padding
-                        if (lane < kTPP)
-                            tma_load_5d(sa + lane * kTileBytes, &tmap, 16 * g, (dx + 1) & 1, (dx + 1) / 2 - 1,
-                                        2 * (tile0 + lane) * rows_per_tile + dy - 1, (int)n, full_bar(slot));
+                        if (lane < NBOX)
+                            tma_load_5d(sa + (bh * kTPP + bt) * kTileBytes, &tmap, 16 * g, (dx + 1) & 1, (dx + 1) / 2 - 1,
+                                        2 * (tile0 + bt) * rows_per_tile + dy - 1, (int)n, full_bar(slot));
                         else if (!(UMMA_DBG & 4))
-                            bulk_g2s(sa + Sh::BOFF, a.wst + (size_t)s * (Sh::B_BYTES / 4), Sh::B_BYTES, full_bar(slot));
+                            bulk_g2s(sa + Sh::BOFF, a.wst + (size_t)s * (Sh::SUB * Sh::B_BYTES / 4), Sh::SUB * Sh::B_BYTES, full_bar(slot));
                     }
                 }
             }
@@ -446,7 +455,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         const int q = warp & 3, t = (warp - kBuild0 / 32) >> 2;
         const int r = 32 * q + lane;
         const uint32_t rowoff = (uint32_t)t * kTileBytes + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
-        const uint32_t tdst = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(Sh::ABASE + t * 32);
+        const uint32_t tdst = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(Sh::ABASE + t * 32 * Sh::SUB);
         const long long my_passes = p_end - p_begin;
         const long long total = my_passes * S;
         uint32_t it = 0;
@@ -457,19 +466,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             mbar_wait_relaxed(loempty_bar(ls), ((it / NL) & 1u) ^ 1u);
             tc_fence_after();
             if (!(UMMA_DBG & 2)) {
-                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(hi[4 * c]), "=r"(hi[4 * c + 1]), "=r"(hi[4 * c + 2]), "=r"(hi[4 * c + 3])
-                                 : "r"(sa + (((uint32_t)c ^ sw) << 4)));
+                for (int h = 0; h < Sh::SUB; ++h) {
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float l = __uint_as_float(hi[k]) - __uint_as_float(hi[k] & 0xFFFFE000u);
-                    lo[k] = (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
+                    for (int c = 0; c < 4; ++c)
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(hi[4 * c]), "=r"(hi[4 * c + 1]), "=r"(hi[4 * c + 2]), "=r"(hi[4 * c + 3])
+                                     : "r"(sa + (uint32_t)(h * kTPP) * kTileBytes + (((uint32_t)c ^ sw) << 4)));
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float l = __uint_as_float(hi[k]) - __uint_as_float(hi[k] & 0xFFFFE000u);
+                        lo[k] = (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
+                    }
+                    tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS + h * 32), hi);
+                    tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS + h * 32) + 16, lo);
                 }
-                tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS), hi);
-                tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS) + 16, lo);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
             tc_fence_before();
