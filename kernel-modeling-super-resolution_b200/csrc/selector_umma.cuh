@@ -335,7 +335,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // One thread per M tile of the pass: the MMAs here are small (32-128 clocks of tensor time each) and a thread needs
         // ~50-90 clocks to issue one (uniform-register descriptor moves, elect, branch), so a single issuer was the limiter
         // (ncu: 80 % of its samples in the issue sequence).  Descriptors are the slot-0 descriptor plus constants.
-        if (lane == 0) {
+        uint32_t leader;
+        asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(leader));
+        {
             const int t = warp == kMmaWarp ? 0 : 1;
             constexpr uint32_t idesc_cat = idesc_tf32(2 * COUT), idesc_one = idesc_tf32(COUT);
             constexpr uint64_t kJB = (2 * Sh::B_LBO) >> 4;                                      // second k-step of a stage, B
@@ -354,7 +356,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     mbar_wait(lofull_bar(ls), (it / NL) & 1u);
                     tc_fence_after();
                     const uint64_t bd = b0 + (uint64_t)((slot * Sh::SLOT) >> 4);
-                    if (!(UMMA_DBG & 1)) {
+                    if (!(UMMA_DBG & 1) && leader) {
                         // A from tensor memory: columns [hi 16 | lo 16] per sub-stage of this tile in slot ls, 8 per k-step
 #pragma unroll
                         for (int h = 0; h < Sh::SUB; ++h) {
@@ -375,10 +377,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                             }
                         }
                     }
-                    mma_commit(empty_bar(slot));                       // arrives once these MMAs have read the slot's weights
-                    mma_commit(loempty_bar(ls));                       // ... and the A slot
+                    if (leader) {
+                        mma_commit(empty_bar(slot));                   // arrives once these MMAs have read the slot's weights
+                        mma_commit(loempty_bar(ls));                   // ... and the A slot
+                    }
+                    __syncwarp();
                 }
-                mma_commit(tfull_bar(buf));                            // ... and once the accumulators are final
+                if (leader) mma_commit(tfull_bar(buf));                // ... and once the accumulators are final
             }
         }
     } else if (warp == kTmaWarp) {
