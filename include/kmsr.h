@@ -276,7 +276,7 @@ KMSR_API int kmsr_selector_logits(const float* x, int64_t N, int H, int W,
                                   float* logits, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The same logits through the 5th-generation tensor cores (csrc/selector_umma.cuh: tcgen05.mma kind::tf32, accumulators
- * in tensor memory, the activations of layers 2 / 3 fetched as strided TMA boxes, 3xTF32 split as two MMAs per k-step).
+ * and the A operand in tensor memory, the activations of layers 2 / 3 fetched as strided TMA boxes, 3xTF32 split).
  * Shapes: kmsr_selector_umma_supported(H, W) != 0 (H, W multiples of 8, W in {64, 128, 256}, an even number of 128-pixel
  * tiles per layer; 256 x 256 and 128 x 128 patches qualify).  Weight blobs are the per-stage shared-memory images
  * [stage][4][2 cout / 8][8][4] (rows < cout: TF32 hi part, rows >= cout: lo part; kmsr_b200/selector.py builds them),

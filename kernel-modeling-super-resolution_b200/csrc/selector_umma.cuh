@@ -1,33 +1,28 @@
 // selector_umma.cuh -- SelectorNet convolutions (muti_kernel/train_gemini.py:14-39) on the 5th-generation tensor cores:
-// `tcgen05.mma.kind::tf32` with the accumulators in tensor memory, SURVEY.md 8f row f2, round 2.  DESIGN.md 4.8.
+// `tcgen05.mma.kind::tf32` with the accumulators AND the A operand in tensor memory, SURVEY.md 8f row f2, round 2.
+// DESIGN.md 4.8 has the design, the probes behind it and the measurements.
 //
 // A 3x3 / stride-2 / pad-1 convolution is the GEMM  D[pixel, cout] = sum_k A[pixel, k] B[cout, k],  k = (tap, cin).
-// One MMA tile is 128 output pixels (raster order inside a patch) x COUT channels; K is walked in stages of 16 (two MMA
-// k-steps of 8).  fp32-level accuracy comes from the 3xTF32 split, arranged so that two MMAs do the work of three:
-//     D[:, 0:2C]  += A_hi x [B_hi ; B_lo]^T      (N = 2 COUT: hi*hi in columns 0..C-1, hi*lo in columns C..2C-1)
-//     D[:, 0:C]   += A_lo x  B_hi^T              (N = COUT, accumulated onto the hi*hi columns)
-// and the epilogue adds the two column halves.
+// One MMA tile is 128 output pixels (raster order inside a patch) x COUT channels, M = 128, K = 8 per instruction.
+// fp32-level accuracy comes from the 3xTF32 split a_hi b_hi + a_hi b_lo + a_lo b_hi.  The tensor core truncates an fp32
+// operand to TF32 (scratch/umma_round_probe.cu), so the raw activations ARE A_hi and A_lo = rna_tf32(x - trunc_tf32(x)).
+// Builder threads (one row of one tile each) write 16 hi and 16 lo values per K = 16 sub-stage into a short ring of A
+// slots in tensor memory (tcgen05.st); the MMAs are TS-form (A from tensor memory, the weights [B_hi ; B_lo] from shared
+// memory in the K-major canonical layout without swizzle, host-built, streamed per stage with one bulk copy).
+// Layers 2 / 3 (channel-last activations): the builders read TMA boxes -- 16 channels x Wo pixels (every second column)
+// x 128 / Wo rows (every second row), 64-byte swizzle, zero fill outside the image = the padding.  First layer
+// ([N, 5, H, W]): the input rows of a pass arrive as one TMA box, the builders gather their taps from it.
 //
-// The tensor core truncates an fp32 operand to TF32 (scratch/umma_round_probe.cu), so the raw activations ARE A_hi and
-// A_lo = rna_tf32(x - trunc_tf32(x)).  Layers 2 / 3 (channel-last activations): A_hi arrives as TMA boxes in the operand
-// layout itself -- 16 channels x Wo pixels (every second column) x 128 / Wo rows (every second row), 64-byte swizzle,
-// zero fill outside the image = the padding; the descriptor is K-major SWIZZLE_64B.  A_lo is built from the landed tile
-// by the builder warps (the lo tile mirrors the hi tile byte for byte).  The weights [B_hi ; B_lo] stream per stage as one
-// bulk copy of the host-built shared-memory image (K-major canonical layout without swizzle).  First layer ([N, 5, H, W]
-// input): a 16-byte operand chunk is four taps of one pixel, which no box produces: threads gather hi and lo tiles.
-//
-// Warp roles (480 threads, one persistent CTA per SM):
-//   warps 0-3   epilogue: tcgen05.ld of the tile (TMEM lane quadrant = warp), halves added, + bias, ReLU, then either the
-//               tile staged in swizzled shared memory and written by TMA stores (two staging buffers in rotation) or --
-//               last layer -- the per-tile channel sums (shuffle reduce-scatter, fixed order, deterministic) that
-//               pool_fc_kernel turns into logits
-//   warps 4, 14 one thread each issues the MMAs of one M tile of the pass and the commits that release ring slots /
-//               publish the accumulator buffer
-//   warp  5     layers 2 / 3: TMA producer (three lanes: the two tiles' boxes and the weight stage)
-//   warps 6-13  operand builders: lo tiles from the landed hi tiles (layers 2 / 3), or the gather of both tiles (layer 1:
-//               four groups of two warps, one ring slot each)
-// A pass = two M tiles sharing every weight stage; accumulators are double-buffered in TMEM when 8 COUT <= 512 columns.
-// Rings: layers 2 / 3 a deep ring of TMA landing slots [hi 0 | hi 1 | B] and a short ring of lo slots; layer 1 one ring.
+// Warp roles (480 threads, one persistent CTA per SM, a contiguous run of passes each):
+//   warps 0-3   epilogue: tcgen05.ld of the tile (TMEM lane quadrant = warp), + bias, ReLU, then either the tile staged
+//               in swizzled shared memory and written by TMA stores (two staging buffers in rotation) or -- last layer --
+//               the per-tile channel sums (shuffle reduce-scatter, fixed order, deterministic) that pool_fc_kernel turns
+//               into logits
+//   warps 4, 14 MMA issue, one warp per M tile of the pass, warp-uniform code (elect.sync once): UTCHMMA back to back,
+//               tcgen05.commit releases ring slots / publishes the accumulator buffer
+//   warp  5     producer: a lane per TMA request of a stage (boxes, weight stage; first layer: input rows per pass)
+//   warps 6-13  A-operand builders
+// A pass = two M tiles sharing every weight stage; accumulators are double-buffered where 512 columns allow it.
 #pragma once
 #include <string.h>
 

@@ -430,7 +430,7 @@ def selector_pick(args, rank, world, dev):
     lg = sel.logits(torch.from_numpy(hg).to(dev), algo="umma").cpu().numpy()
     flop = 2.0 * n * (128 * 128 * 32 * 45 + 64 * 64 * 64 * 288 + 32 * 32 * 128 * 576)
     return {"row": "f2", "workload": f"SelectorNet pick of {n} patches [5,256,256] per GPU (3 convolutions + pooling + linear layer)",
-            "algo": "tcgen05 (kind::tf32, TMEM accumulators, 3xTF32 split as two MMAs per k-step)",
+            "algo": "tcgen05 (kind::tf32, accumulators and A operand in tensor memory, 3xTF32 split)",
             "ms_tcgen05": ms_umma, "ms_mma_sync": ms_mma, "ms_library_fp32": ms_lib, "ms_fused_degrade": ms_deg,
             "patches_per_s": n * world / (ms_umma * 1e-3), "useful_tflops": flop / (ms_umma * 1e-3) / 1e12,
             "tensor_tflops_3x": 3 * flop / (ms_umma * 1e-3) / 1e12,
