@@ -378,6 +378,28 @@ def test_selector_tcgen05_weight_stages_reproduce_the_reference_forward(golden):
     assert np.array_equal(lg.argmax(1), ref.argmax(1))
 
 
+def test_selector_tcgen05_host_queries():
+    """The shape / size queries of the tcgen05 selector path are plain host functions of the C ABI (no device needed):
+    which patch shapes the path takes, the weight-stage sizes selector.py must produce, the workspace (channel-last
+    activations of layers 1 / 2 + per-tile channel sums), and the error code for shapes it refuses."""
+    from kmsr_b200 import _lib as L
+    lib = L.lib()
+    ok = [(256, 256), (128, 128), (64, 256), (256, 128), (512, 256), (256, 64)]
+    no = [(100, 100), (17, 33), (128, 64), (256, 512), (8, 8), (250, 256)]
+    assert all(lib.kmsr_selector_umma_supported(h, w) == 1 for h, w in ok)
+    assert all(lib.kmsr_selector_umma_supported(h, w) == 0 for h, w in no)
+    # [stage][4 chunks][2 cout / 8][8][4] floats: 3 stages for the 5-band layer, 9 cin / 16 otherwise
+    assert lib.kmsr_selector_umma_weight_floats(5, 32) == 3 * 4 * 64 * 4
+    assert lib.kmsr_selector_umma_weight_floats(32, 64) == 18 * 4 * 128 * 4
+    assert lib.kmsr_selector_umma_weight_floats(64, 128) == 36 * 4 * 256 * 4
+    assert lib.kmsr_selector_umma_weight_floats(7, 32) < 0 and lib.kmsr_selector_umma_weight_floats(32, 20) < 0
+    n = 10
+    ws = lib.kmsr_selector_umma_workspace_bytes(n, 256, 256)
+    need = n * (128 * 128 * 32 + 64 * 64 * 64 + 8 * 128) * 4
+    assert need <= ws <= need + 4 * 256
+    assert lib.kmsr_selector_umma_workspace_bytes(n, 100, 100) == L.KMSR_E_INVALID if hasattr(L, "KMSR_E_INVALID") else lib.kmsr_selector_umma_workspace_bytes(n, 100, 100) < 0
+
+
 def test_reference_arm_loader_prefers_the_verbatim_reference(monkeypatch, tmp_path):
     """oracle/refarm.py: the verbatim reference function when a copy is reachable (KMSR_REFERENCE_ROOT, baseline/_ref,
     /root/reference), else the call-site port -- and both give the same pairs on the same inputs."""
