@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel SASS opcode histogram of libkmsr.so (cuobjdump -sass): what proves the kernels are sm_100a code
 (UTMALDG = cp.async.bulk.tensor, UBLKCP = cp.async.bulk, SYNCS = mbarrier, FFMA2 / FADD2 = packed fp32, HMMA =
-mma.sync of the selector's fallback path; UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTMASTG = TMA store
+mma.sync of the selector's fallback path; UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTCBAR = tcgen05.commit, UTMASTG = TMA store
 of the selector's tcgen05 path).  python tools/sass_ops.py > profiles/sass_ops.txt"""
 import collections
 import os
@@ -15,7 +15,7 @@ txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
 arch = sorted(set(re.findall(r"arch = (sm_\w+)", txt)))
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
 print(f"# {os.path.relpath(so, ROOT)}: {len(funcs)} kernels, arch {', '.join(arch)}; opcode counts are static (per SASS listing)")
-KEY = ["UTMALDG", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "HMMA", "LDGSTS", "LDS", "STS", "LDG", "STG", "SHFL", "BAR", "UTCHMMA", "LDTM", "UTCBAR", "UTMASTG"]
+KEY = ["UTMALDG", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "HMMA", "LDGSTS", "LDS", "STS", "LDG", "STG", "SHFL", "BAR", "UTCHMMA", "LDTM", "STTM", "UTCBAR", "UTMASTG"]
 print("# kernel | instructions | " + " ".join(KEY))
 tot = collections.Counter()
 for f in sorted(funcs, key=lambda f: f.split("\n")[0]):
