@@ -861,7 +861,7 @@ def test_selector_tcgen05_path(K, golden, synth):
     z = golden("selector.npz")
     sel = Selector.from_npz(z, "cuda")
     worst = 0.0
-    for n, h, w in ((6, 256, 256), (301, 256, 256), (5, 128, 128), (3, 64, 256), (4, 256, 128), (2, 512, 256), (3, 256, 64)):
+    for n, h, w in ((6, 256, 256), (1, 256, 256), (301, 256, 256), (5, 128, 128), (3, 64, 256), (4, 256, 128), (2, 512, 256), (3, 256, 64)):
         assert K.lib.lib().kmsr_selector_umma_supported(h, w) == 1, (h, w)
         rs = np.random.RandomState(h + w)
         x = torch.from_numpy((rs.standard_normal((n, 5, h, w)) * 3.0 + np.array([80, 70, 50, 25, 8])[None, :, None, None])
