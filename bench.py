@@ -489,9 +489,10 @@ def main():
         torch.cuda.empty_cache()
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import run_configs as rc
-        ns_ = argparse.Namespace(reps=3, c3_patches=12500, c3_check=256, c4_size=8192, c4_scene_per_rank=True, c5_gb=1.0,
-                                 c5_algos="", c5_cells=[(31, 64, 8), (21, 64, 8), (15, 256, 4), (13, 256, 2), (31, 256, 2),
-                                                        (11, 512, 8), (13, 512, 8)])
+        # config 5: the whole 60-cell sweep at 4 GB of HR patches per cell (a few seconds; the same command line as
+        # tests/run_configs.py --configs 5 --c5-gb 4, whose output is profiles/r2_configs.json)
+        ns_ = argparse.Namespace(reps=3, c3_patches=12500, c3_check=256, c4_size=8192, c4_scene_per_rank=True, c5_gb=4.0,
+                                 c5_algos="", c5_cells=None)
         configs = {}
         ns_.sel_patches = 4096
         for name, f in (("config3", rc.config3), ("config4", rc.config4), ("f2_selector", rc.selector_pick)) + \

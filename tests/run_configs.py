@@ -402,8 +402,12 @@ def config5(args, rank, world, dev):
             ref = orc.apply_kernel_degradation(torch.from_numpy(h[i]), torch.from_numpy(kern), s).numpy()
             e = max(e, float((np.abs(lr[i].astype(np.float64) - ref) / orc.band_range(h[i])).max()))
         par.append({"k": k, "P": p, "s": s, "ours_vs_ref": e})
+    fr = sorted(max(r["hbm_frac"], r["fp32_frac"]) for r in rows)
+    summary = {"cells": len(fr), "hr_gb_per_cell": args.c5_gb, "binding_roofline_frac_median": fr[len(fr) // 2] if len(fr) % 2 else
+               0.5 * (fr[len(fr) // 2 - 1] + fr[len(fr) // 2]), "min": fr[0], "max": fr[-1],
+               "cells_ge_0.70": sum(f >= 0.70 for f in fr), "cells_ge_0.50": sum(f >= 0.50 for f in fr), "cells_lt_0.35": sum(f < 0.35 for f in fr)}
     return {"config": 5, "workload": "roofline sweep k x P x s, 1 GPU", "hbm_peak_gbs": HBM_PEAK,
-            "fp32_peak_tflops": FP32_PEAK_TFLOPS, "fp32_peak_source": fp32_src,
+            "fp32_peak_tflops": FP32_PEAK_TFLOPS, "fp32_peak_source": fp32_src, "summary": summary,
             "rows": rows, "parity": par, "bar": 1e-5}
 
 
