@@ -5,7 +5,7 @@
 // A 3x3 / stride-2 / pad-1 convolution is the GEMM  D[pixel, cout] = sum_k A[pixel, k] B[cout, k],  k = (tap, cin).
 // One MMA tile is 128 output pixels (raster order inside a patch) x COUT channels, M = 128, K = 8 per instruction.
 // fp32-level accuracy comes from the 3xTF32 split a_hi b_hi + a_hi b_lo + a_lo b_hi.  The tensor core truncates an fp32
-// operand to TF32 (scratch/umma_round_probe.cu), so the raw activations ARE A_hi and A_lo = rna_tf32(x - trunc_tf32(x)).
+// operand to TF32 (scratch/umma_round_probe.cu), so the raw activations ARE A_hi and A_lo = x - trunc_tf32(x) (exact).
 // Builder threads (one row of one tile each) write 16 hi and 16 lo values per K = 16 sub-stage into a short ring of A
 // slots in tensor memory (tcgen05.st); the MMAs are TS-form (A from tensor memory, the weights [B_hi ; B_lo] from shared
 // memory in the K-major canonical layout without swizzle, host-built, streamed per stage with one bulk copy).
@@ -451,7 +451,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         // builder warps take tile 0, the other four tile 1.  Per stage it reads its 64-byte row of the landed (64-byte
         // swizzled) tile -- chunk c at position c ^ ((row >> 1) & 3): conflict free over a quarter-warp -- and writes 16 hi
         // and 16 lo values to tensor memory.  hi = x as it is (the MMA truncates it to TF32); lo = x - trunc(x) is exact in
-        // fp32 and is rounded to TF32 here (ties away, two integer instructions).
+        // fp32 and is stored as it is: the MMA truncates it too, an error of at most 2^-21 |x|, below the lo * lo term the
+        // split drops anyway (rounding it here cost two more integer instructions per value and 3 % of the layer).
         const int q = warp & 3, t = (warp - kBuild0 / 32) >> 2;
         const int r = 32 * q + lane;
         const uint32_t rowoff = (uint32_t)t * kTileBytes + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
@@ -477,7 +478,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         const float l = __uint_as_float(hi[k]) - __uint_as_float(hi[k] & 0xFFFFE000u);
-                        lo[k] = (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
+                        lo[k] = __float_as_uint(l);
                     }
                     tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS + h * 32), hi);
                     tmem_st16(tdst + (uint32_t)(ls * Sh::ACOLS + h * 32) + 16, lo);
@@ -543,7 +544,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         const float l = __uint_as_float(hi[k]) - __uint_as_float(hi[k] & 0xFFFFE000u);
-                        lo[k] = (__float_as_uint(l) + 0x1000u) & 0xFFFFE000u;
+                        lo[k] = __float_as_uint(l);
                     }
                 }
                 mbar_wait_relaxed(loempty_bar(ls), ((it / NL) & 1u) ^ 1u);
