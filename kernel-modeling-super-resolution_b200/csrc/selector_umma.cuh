@@ -9,8 +9,8 @@
 // Builder threads (one row of one tile each) write 16 hi and 16 lo values per K = 16 sub-stage into a short ring of A
 // slots in tensor memory (tcgen05.st); the MMAs are TS-form (A from tensor memory, the weights [B_hi ; B_lo] from shared
 // memory in the K-major canonical layout without swizzle, host-built, streamed per stage with one bulk copy).
-// Layers 2 / 3 (channel-last activations): the builders read TMA boxes -- 16 channels x Wo pixels (every second column)
-// x 128 / Wo rows (every second row), 64-byte swizzle, zero fill outside the image = the padding.  First layer
+// Layers 2 / 3 (channel-last activations): the builders read TMA boxes -- 32 channels x Wo pixels (every second column)
+// x 128 / Wo rows (every second row), 128-byte swizzle, zero fill outside the image = the padding.  First layer
 // ([N, 5, H, W]): the input rows of a pass arrive as one TMA box, the builders gather their taps from it.
 //
 // Warp roles (480 threads, one persistent CTA per SM, a contiguous run of passes each):
@@ -416,11 +416,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             }
         } else {
             // one lane per request of a stage (a single thread sustains about one TMA request per 280 ns): lanes
-            // 0 .. 3 the boxes (sub-stage, tile), lane 4 the weight stages; lane 0 also posts the byte count
-            constexpr int NBOX = Sh::SUB * kTPP, GS = G / Sh::SUB;
+            // 0 / 1 the two tiles' boxes, lane 2 the weight stages; lane 0 also posts the byte count.  A box row is the 32
+            // channels of the stage (128 bytes, 128-byte swizzle): the TMA engine needs ~2.7 clocks per box row whatever its
+            // length, so 64-byte rows made the feed twice as expensive
+            constexpr int NBOX = kTPP, GS = G / Sh::SUB;
+            static_assert(Sh::SUB == 2, "a box row is two K = 16 sub-stages");
             if (lane < NBOX + 1) {
                 const int rows_per_tile = 128 / a.Wo;                  // output rows of one M tile
-                const int bt = lane % kTPP, bh = lane / kTPP;          // this lane's box: tile, sub-stage
+                const int bt = lane;                                   // this lane's box: tile
                 uint32_t it = 0;
                 for (long long pass = p_begin; pass < p_end; ++pass) {
                     const long long n = pass / half_tiles;
@@ -429,15 +432,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     for (int s = 0; s < S; ++s, ++it) {
                         const int slot = (int)(it % NH);
                         const uint32_t sa = base + slot * Sh::SLOT;
-                        const int tap = s / GS, g = (s - tap * GS) * Sh::SUB + bh;       // 16-channel group of this lane's box
+                        const int tap = s / GS, g = s - tap * GS;             // 32-channel group of the stage
                         const int dy = tap / 3, dx = tap - 3 * dy;
                         mbar_wait(empty_bar(slot), ((it / NH) & 1u) ^ 1u);
                         if (lane == 0)
-                            mbar_arrive_expect_tx(full_bar(slot), NBOX * kTileBytes + ((UMMA_DBG & 4) ? 0u : Sh::SUB * Sh::B_BYTES));
-                        // the raw fp32 activations ARE the hi operand (the tensor core reads the upper 19 bits): box = 16 channels
+                            mbar_arrive_expect_tx(full_bar(slot), NBOX * Sh::SUB * kTileBytes + ((UMMA_DBG & 4) ? 0u : Sh::SUB * Sh::B_BYTES));
+                        // the raw fp32 activations ARE the hi operand (the tensor core reads the upper 19 bits): box = 32 channels
                         // x Wo pixels at stride 2 x (128 / Wo) rows at stride 2, zero-filled outside the image = the padding
                         if (lane < NBOX)
-                            tma_load_5d(sa + (bh * kTPP + bt) * kTileBytes, &tmap, 16 * g, (dx + 1) & 1, (dx + 1) / 2 - 1,
+                            tma_load_5d(sa + bt * Sh::SUB * kTileBytes, &tmap, 32 * g, (dx + 1) & 1, (dx + 1) / 2 - 1,
                                         2 * (tile0 + bt) * rows_per_tile + dy - 1, (int)n, full_bar(slot));
                         else if (!(UMMA_DBG & 4))
                             bulk_g2s(sa + Sh::BOFF, a.wst + (size_t)s * (Sh::SUB * Sh::B_BYTES / 4), Sh::SUB * Sh::B_BYTES, full_bar(slot));
@@ -448,14 +451,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     } else if constexpr (TMA) {
         // ------------------------------------------------------------------------------------------ A-operand builders (layers 2 / 3)
         // A thread owns one row (output pixel) of one M tile: warp % 4 is the TMEM lane quadrant it may write, the first four
-        // builder warps take tile 0, the other four tile 1.  Per stage it reads its 64-byte row of the landed (64-byte
-        // swizzled) tile -- chunk c at position c ^ ((row >> 1) & 3): conflict free over a quarter-warp -- and writes 16 hi
+        // builder warps take tile 0, the other four tile 1.  Per stage it reads its 128-byte row of the landed (128-byte
+        // swizzled) tile -- chunk c at position c ^ (row & 7): conflict free over a quarter-warp -- and writes 16 hi
         // and 16 lo values to tensor memory.  hi = x as it is (the MMA truncates it to TF32); lo = x - trunc(x) is exact in
         // fp32 and is stored as it is: the MMA truncates it too, an error of at most 2^-21 |x|, below the lo * lo term the
         // split drops anyway (rounding it here cost two more integer instructions per value and 3 % of the layer).
         const int q = warp & 3, t = (warp - kBuild0 / 32) >> 2;
         const int r = 32 * q + lane;
-        const uint32_t rowoff = (uint32_t)t * kTileBytes + (uint32_t)r * 64u, sw = ((uint32_t)r >> 1) & 3u;
+        const uint32_t rowoff = (uint32_t)t * Sh::SUB * kTileBytes + (uint32_t)r * 128u, sw = (uint32_t)r & 7u;
         const uint32_t tdst = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(Sh::ABASE + t * 32 * Sh::SUB);
         const long long my_passes = p_end - p_begin;
         const long long total = my_passes * S;
@@ -474,7 +477,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                     for (int c = 0; c < 4; ++c)
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                                      : "=r"(hi[4 * c]), "=r"(hi[4 * c + 1]), "=r"(hi[4 * c + 2]), "=r"(hi[4 * c + 3])
-                                     : "r"(sa + (uint32_t)(h * kTPP) * kTileBytes + (((uint32_t)c ^ sw) << 4)));
+                                     : "r"(sa + (((uint32_t)(4 * h + c) ^ sw) << 4)));
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
                         const float l = __uint_as_float(hi[k]) - __uint_as_float(hi[k] & 0xFFFFE000u);
@@ -585,16 +588,16 @@ int launch_conv_umma(const ConvUArgs& a, long long N, int sms, cudaStream_t st) 
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled (input rows) failed with CUresult %d", (int)cr);
     } else {
-        // channel-last activations [N, H, W, CIN] seen as (c, x, y, n); one box = one 128-pixel M tile of one 16-channel
-        // group of one tap: 16 channels x Wo pixels (every second column) x 128 / Wo rows (every second row), 64-byte swizzle
+        // channel-last activations [N, H, W, CIN] seen as (c, x parity, x / 2, y, n); one box = one 128-pixel M tile of one
+        // 32-channel group of one tap: 32 channels x Wo pixels (one column parity) x 128 / Wo rows (every second row), 128-byte swizzle
         EncodeTiledFn enc = get_tensor_map_encoder();
         KMSR_REQUIRE(enc != nullptr, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled is not available");
         cuuint64_t gdim[5] = {(cuuint64_t)CIN, 2, (cuuint64_t)(a.W / 2), (cuuint64_t)a.H, (cuuint64_t)N};
         cuuint64_t gstr[4] = {(cuuint64_t)CIN * 4, (cuuint64_t)CIN * 8, (cuuint64_t)a.W * CIN * 4, (cuuint64_t)a.H * a.W * CIN * 4};
-        cuuint32_t box[5] = {16, 1, (cuuint32_t)a.Wo, (cuuint32_t)(2 * (128 / a.Wo)), 1};
+        cuuint32_t box[5] = {32, 1, (cuuint32_t)a.Wo, (cuuint32_t)(2 * (128 / a.Wo)), 1};
         cuuint32_t estr[5] = {1, 1, 1, 2, 1};
         CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)a.in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         KMSR_REQUIRE(cr == CUDA_SUCCESS, KMSR_E_CUDA, "selector (tcgen05): cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
     }
     CUtensorMap omap;
