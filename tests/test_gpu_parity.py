@@ -890,6 +890,23 @@ def test_selector_tcgen05_path(K, golden, synth):
         assert np.isnan(ln[1]).all() and np.isfinite(ln[[0, 2, 3, 4, 5]]).all(), algo
         if algo == "umma":
             assert np.array_equal(ln[[0, 2, 3, 4, 5]], lg[[0, 2, 3, 4, 5]])
+    # the C ABI directly: argument errors come back as codes, nothing is launched
+    import ctypes as C
+    lib = K.lib.lib()
+    sel._prepare_umma(torch.device("cuda", torch.cuda.current_device())) if sel._umma is None else None
+    _, blobs, fc_w, fc_b = sel._umma
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    xs = torch.zeros((2, 5, 256, 256), device="cuda")
+    out = torch.zeros((2, 10), device="cuda")
+    need = lib.kmsr_selector_umma_workspace_bytes(2, 256, 256)
+    ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+    args = lambda x_, ws_, n_ws: (vp(x_), 2, 256, 256, vp(blobs[0][0]), vp(blobs[0][1]), vp(blobs[1][0]), vp(blobs[1][1]),
+                                  vp(blobs[2][0]), vp(blobs[2][1]), vp(fc_w), vp(fc_b), vp(out), ws_, n_ws, None)
+    assert lib.kmsr_selector_logits_umma(*args(xs, vp(ws), need)) == 0
+    assert lib.kmsr_selector_logits_umma(*args(xs, vp(ws), need - 1)) == K.lib.E_INVALID and "workspace" in K.lib.last_error()
+    assert lib.kmsr_selector_logits_umma(*args(xs, None, need)) == K.lib.E_INVALID
+    assert lib.kmsr_selector_logits_umma(*args(xs.view(-1)[1:], vp(ws), need)) == K.lib.E_ALIGN      # x not 16-byte aligned
+    assert lib.kmsr_selector_logits_umma(vp(xs), 2, 100, 100, *args(xs, vp(ws), need)[4:]) == K.lib.E_UNSUPPORTED
     # shapes outside the path
     for h, w in ((100, 100), (17, 33), (128, 64), (256, 512)):
         assert K.lib.lib().kmsr_selector_umma_supported(h, w) == 0
