@@ -507,6 +507,13 @@ def main():
             torch.cuda.empty_cache()
         if world > 1:
             configs["config5"] = {"skipped": "single-GPU sweep: measured at N = 1 only"}
+        elif "rows" in configs.get("config5", {}):
+            # keep the one-line JSON short: a row as [k, P, s, algo, ms, hbm_frac, fp32_frac] (the full rows of the same
+            # command are tests/run_configs.py --configs 5 --c5-gb 4 -> profiles/r2_configs.json)
+            c5 = configs["config5"]
+            c5["columns"] = ["k", "P", "s", "algo", "ms", "hbm_frac", "fp32_frac"]
+            c5["rows"] = [[r["k"], r["P"], r["s"], r["algo"], round(r["ms"], 4), round(r["hbm_frac"], 4), round(r["fp32_frac"], 4)]
+                          for r in c5["rows"]]
 
     if rank == 0:
         peak, peak_src = measured_peak()
